@@ -1,0 +1,258 @@
+"""Generate ``tests/golden/*.npz`` by running the UNMODIFIED reference here.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (which has
+``/root/reference``):  ``python -m oracle.make_golden``.  The GPU box never runs
+this; it only reads the committed vectors.
+
+Each vector records inputs and the reference's own outputs for one piece of
+the path.  scikit-image functions inside are ``oracle.skimage_restated`` (see
+``oracle/ref_shim.py``), so what these vectors pin is the reference's Python:
+chunk geometry, block setup, blob table layout, per-chunk orchestration, seam
+pruning, saturate/denoise glue.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim                     # noqa: E402
+from magellanmapper_b200 import synth           # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _slices_to_arr(sl):
+    arr = np.zeros(sl.shape + (3, 2), dtype=np.int64)
+    for c in np.ndindex(*sl.shape):
+        arr[c] = [[s.start, s.stop] for s in sl[c]]
+    return arr
+
+
+def gen_chunk_geometry(ns):
+    cases = [
+        ((5, 4, 4), (1, 3, 3), (0, 1, 1)),        # magmap/tests/test_chunking.py
+        ((5, 4, 4), (1, 3, 3), (0, 1, 2)),
+        ((5, 4, 4), (1, 3, 3), (1, 1, 2)),
+        ((5, 4, 4), (1, 3, 3), (1, 3, 3)),        # calc_overlap(2) at res 6.6,1.1,1.1 -> ceil(2/res)
+        ((512, 2048, 2048), (500, 500, 500), (5, 5, 5)),   # BASELINE config 2
+        ((1024, 4096, 4096), (100, 500, 500), (1, 5, 5)),  # config 5
+        ((60, 128, 128), (50, 50, 50), None),
+        ((50, 500, 500), (25, 25, 25), None),
+        ((7, 7, 7), (10, 10, 10), (2, 2, 2)),
+    ]
+    out = {}
+    for i, (shape, mp_, ov) in enumerate(cases):
+        sl, off = ns.chunking.stack_splitter(shape, mp_, None if ov is None else np.array(ov))
+        out[f"c{i}_shape"] = np.array(shape)
+        out[f"c{i}_max_pixels"] = np.array(mp_)
+        out[f"c{i}_overlap"] = np.array(ov if ov is not None else (-1, -1, -1))
+        out[f"c{i}_slices"] = _slices_to_arr(sl)
+        out[f"c{i}_offsets"] = off
+    out["n"] = np.array(len(cases))
+    # calc_overlap / calc_scaling_factor
+    ns.config.resolutions = [[6.6, 1.1, 1.1]]
+    out["overlap2_res661111"] = ns.detector.calc_overlap(2)
+    out["overlap_default_res661111"] = ns.detector.calc_overlap()
+    np.savez_compressed(os.path.join(OUT, "chunk_geometry.npz"), **out)
+
+
+def gen_setup_blocks(ns):
+    out = {}
+    cases = [
+        ((512, 2048, 2048), (1, 1, 1), {}),
+        ((1024, 4096, 4096), (5, 1, 1), {}),
+        ((51, 200, 200), (6.6, 1.1, 1.1), {"exclude_border": (1, 0, 0), "segment_size": 150,
+                                            "prune_tol_factor": (1, 0.9, 0.9)}),
+        ((60, 128, 128), (1, 1, 1), {"segment_size": 50}),
+        ((60, 128, 128), (1, 1, 1), {"segment_size": 50, "exclude_border": (4, 3, 0)}),
+    ]
+    for i, (shape, res, mods) in enumerate(cases):
+        prof = ref_shim.set_profile(ns, res, **mods)
+        b = ns.stack_detect.setup_blocks(prof, shape)
+        out[f"b{i}_shape"] = np.array(shape)
+        out[f"b{i}_res"] = np.array(res, dtype=float)
+        out[f"b{i}_mods_keys"] = np.array(list(mods.keys()), dtype=str)
+        for k, v in mods.items():
+            out[f"b{i}_mod_{k}"] = np.array(v, dtype=float)
+        out[f"b{i}_slices"] = _slices_to_arr(b.sub_roi_slices)
+        out[f"b{i}_offsets"] = b.sub_rois_offsets
+        out[f"b{i}_denoise_max_shape"] = np.array(b.denoise_max_shape)
+        out[f"b{i}_tol"] = np.array(b.tol)
+        out[f"b{i}_overlap_base"] = np.array(b.overlap_base)
+        out[f"b{i}_overlap"] = np.array(b.overlap)
+        out[f"b{i}_overlap_padding"] = np.array(b.overlap_padding)
+        out[f"b{i}_max_pixels"] = np.array(b.max_pixels)
+    out["n"] = np.array(len(cases))
+    np.savez_compressed(os.path.join(OUT, "setup_blocks.npz"), **out)
+
+
+def gen_blob_layout(ns):
+    rng = np.random.default_rng(11)
+    b4 = np.column_stack([rng.integers(0, 100, (6, 3)).astype(float),
+                          rng.uniform(3, 9, 6)])
+    bl = ns.detector.Blobs(b4.copy())
+    full = bl.format_blobs(2)
+    cols = np.array(bl.cols, dtype=str)
+    interior = ns.detector.get_blobs_interior(full, (100, 100, 100), (10, 5, 0), (20, 0, 30))
+    np.savez_compressed(os.path.join(OUT, "blob_layout.npz"), b4=b4, full=full,
+                        cols=cols, interior=interior)
+
+
+def _rand_table(rng, n, lo, hi, chunk_tag):
+    """(n, 14) table like merge_blobs output: 11 cols + chunk tag."""
+    t = np.full((n, 14), -1.0)
+    t[:, 0:3] = rng.integers(lo, hi, (n, 3))
+    t[:, 3] = rng.uniform(5, 9, n)
+    t[:, 6] = 0
+    t[:, 7:10] = t[:, 0:3]
+    t[:, 11:14] = chunk_tag
+    return t
+
+
+def gen_remove_close(ns):
+    rng = np.random.default_rng(5)
+    out = {}
+    cases = [(40, 60, (2, 2, 2), 30), (1500, 1200, (1, 3, 3), 60), (5, 0, (1, 1, 1), 10),
+             (300, 300, (5, 5, 5), 400)]
+    for i, (nm, nc, tol, span) in enumerate(cases):
+        master = _rand_table(rng, nm, 0, span, (0, 0, 0))
+        check = _rand_table(rng, nc, 0, span, (1, 0, 0))
+        pruned, master_out = ns.detector.remove_close_blobs(
+            check.copy(), master.copy(), np.array(tol))
+        out[f"r{i}_master"], out[f"r{i}_check"], out[f"r{i}_tol"] = master, check, np.array(tol)
+        out[f"r{i}_pruned"], out[f"r{i}_master_out"] = pruned, master_out
+    out["n"] = np.array(len(cases))
+    np.savez_compressed(os.path.join(OUT, "remove_close.npz"), **out)
+
+
+def gen_prune_mp(ns):
+    """prune_blobs_mp on hand-built per-chunk tables with planted duplicates
+    across all three seam axes."""
+    rng = np.random.default_rng(9)
+    shape = (60, 128, 128)
+    prof = ref_shim.set_profile(ns, (1, 1, 1), segment_size=50)
+    b = ns.stack_detect.setup_blocks(prof, shape)
+    seg = np.zeros(b.sub_roi_slices.shape, dtype=object)
+    base = rng.integers(0, (60, 128, 128), (700, 3)).astype(float)
+    for c in np.ndindex(*seg.shape):
+        sl = b.sub_roi_slices[c]
+        inside = np.all([(base[:, a] >= sl[a].start) & (base[:, a] < sl[a].stop)
+                         for a in range(3)], axis=0)
+        pts = base[inside]
+        # jitter so that duplicates in overlaps are near- but not always exact matches
+        pts = pts + rng.integers(-2, 3, pts.shape)
+        pts = np.clip(pts, [s.start for s in sl], [s.stop - 1 for s in sl])
+        if len(pts) == 0:
+            seg[c] = None
+            continue
+        t = np.full((len(pts), 11), -1.0)
+        t[:, 0:3] = pts
+        t[:, 3] = rng.uniform(5, 9, len(pts))
+        t[:, 6] = 0
+        t[:, 7:10] = pts
+        seg[c] = t
+    roi = np.zeros(shape, dtype=np.uint8)
+    merged = ns.chunking.merge_blobs(seg)
+    pruned, _ = ns.stack_detect.StackPruner.prune_blobs_mp(
+        roi, seg, b.overlap, b.tol, b.sub_roi_slices, b.sub_rois_offsets, [0],
+        b.overlap_padding)
+    out = {"shape": np.array(shape), "merged": merged, "pruned": pruned,
+           "grid": np.array(seg.shape)}
+    for c in np.ndindex(*seg.shape):
+        key = "seg_%d_%d_%d" % c
+        out[key] = seg[c] if seg[c] is not None else np.zeros((0, 11))
+    np.savez_compressed(os.path.join(OUT, "prune_mp.npz"), **out)
+
+
+def gen_preprocess(ns):
+    """saturate_roi + denoise_roi on single blocks (reference glue around
+    np.percentile / gaussian / erosion)."""
+    vol, _ = synth.make_volume((40, 80, 80), seed=21, density=1 / 1500.0)
+    near_max = synth.near_max_of(vol)
+    ref_shim.set_profile(ns, (1, 1, 1), near_max=near_max)
+    rng = np.random.default_rng(3)
+    blocks = {
+        "dense": vol[5:30, 10:35, 20:45],
+        "thin": vol[0:5, 0:25, 0:25],
+        "ragged": vol[28:40, 55:80, 57:80],
+        "constant": np.full((25, 25, 25), 417, dtype=np.uint16),
+        "zeros": np.zeros((6, 7, 8), dtype=np.uint16),
+        "bright": (rng.uniform(20000, 60000, (25, 25, 25))).astype(np.uint16),
+        "two_level": np.where(rng.uniform(size=(25, 25, 25)) < 0.03, 5000, 300).astype(np.uint16),
+        "single_voxel": vol[3:4, 3:4, 3:4],
+    }
+    out = {"near_max": np.array(near_max), "names": np.array(list(blocks), dtype=str)}
+    for name, blk in blocks.items():
+        sat = ns.plot_3d.saturate_roi(blk)
+        den = ns.plot_3d.denoise_roi(sat)
+        out[f"{name}_in"] = blk
+        out[f"{name}_sat"] = sat
+        out[f"{name}_out"] = den
+    np.savez_compressed(os.path.join(OUT, "preprocess_blocks.npz"), **out)
+
+
+def gen_detect_small(ns):
+    """detector.detect_blobs on a raw uint16 ROI and on a preprocessed one,
+    plus an exclude_border call."""
+    vol, tab = synth.make_volume((40, 64, 64), seed=31, density=1 / 3000.0)
+    near_max = synth.near_max_of(vol)
+    ref_shim.set_profile(ns, (1, 1, 1), near_max=near_max)
+    raw = ns.detector.detect_blobs(vol, [0])
+    pre = ns.plot_3d.denoise_roi(ns.plot_3d.saturate_roi(vol))
+    gui = ns.detector.detect_blobs(pre, [0])
+    excl = ns.detector.detect_blobs(pre, [0], np.array([[3, 4, 5], [2, 0, 6]]))
+    np.savez_compressed(os.path.join(OUT, "detect_small.npz"), vol=vol, table=tab,
+                        near_max=np.array(near_max), raw=raw, pre=pre.astype(np.float64),
+                        gui=gui, excl=excl)
+
+
+def gen_stack_small(ns):
+    """stack_detect.detect_blobs_blocks end to end (fork pool, seam pruning) on a
+    multi-chunk volume: segment_size=50 -> 2x3x3 chunks of <=55 px, 25^3
+    preprocessing blocks."""
+    shape = (60, 128, 128)
+    vol, tab = synth.make_volume(shape, seed=41, density=1 / 2500.0)
+    near_max = synth.near_max_of(vol)
+    out = {"vol": vol, "table": tab, "near_max": np.array(near_max)}
+    for tag, mods in (("plain", {"segment_size": 50}),
+                      ("excl", {"segment_size": 50, "exclude_border": (2, 1, 1)})):
+        ref_shim.set_profile(ns, (1, 1, 1), near_max=near_max, **mods)
+        img5d = ns.np_io.Image5d(vol[None])
+        with tempfile.TemporaryDirectory() as td:
+            ns.config.filename = os.path.join(td, "synth")
+            cwd = os.getcwd()
+            os.chdir(td)
+            try:
+                _, _, blobs = ns.stack_detect.detect_blobs_blocks(
+                    ns.config.filename, img5d, None, None, [0], False, False, True)
+            finally:
+                os.chdir(cwd)
+        out[f"{tag}_blobs"] = blobs.blobs
+        out[f"{tag}_cols"] = np.array(blobs.cols, dtype=str)
+    np.savez_compressed(os.path.join(OUT, "stack_small.npz"), **out)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ns = ref_shim.load_reference()
+    gen_chunk_geometry(ns)
+    gen_setup_blocks(ns)
+    gen_blob_layout(ns)
+    gen_remove_close(ns)
+    gen_prune_mp(ns)
+    gen_preprocess(ns)
+    gen_detect_small(ns)
+    gen_stack_small(ns)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()
