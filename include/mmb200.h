@@ -1,0 +1,157 @@
+/* mmb200.h - C ABI of the B200-native MagellanMapper blob-detection library.
+ *
+ * The reference (sanderslab/magellanmapper) is pure Python and has no FFI for
+ * this path; its arithmetic lives in scikit-image / scipy wheels.  Each entry
+ * point below replaces one of those call sites (reference file:line cited) and
+ * is what a ctypes binding on the reference side would load.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no C++/torch types.
+ *   - every function returns 0 on success or a negative MMB_ERR_* code;
+ *     mmb_last_error() returns a thread-local message for the last failure.
+ *   - all volume buffers are CALLER-OWNED DEVICE pointers.  A float volume is
+ *     [Z][Y][pitch] with `pitch >= X` elements per row (rows may be padded).
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it
+ *     unless documented otherwise.
+ *   - variable-length outputs use a caller-sized buffer + a device counter; the
+ *     counter keeps counting past `capacity`, so overflow is detectable and is
+ *     reported (MMB_ERR_OVERFLOW), never silently truncated.
+ */
+#ifndef MMB200_H
+#define MMB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMB_VERSION 1
+
+enum {
+  MMB_OK = 0,
+  MMB_ERR_INVALID = -1,      /* bad argument */
+  MMB_ERR_CUDA = -2,         /* CUDA runtime error, see mmb_last_error() */
+  MMB_ERR_OVERFLOW = -3,     /* candidate / edge buffer too small */
+  MMB_ERR_UNSUPPORTED = -4   /* shape or option outside the implemented range */
+};
+
+/* input voxel types accepted by the converting entry points */
+enum { MMB_U8 = 0, MMB_U16 = 1, MMB_F32 = 2, MMB_F64 = 3 };
+
+/* One local-maximum candidate of the (z, y, x, scale) LoG cube. 20 bytes. */
+typedef struct mmb_cand {
+  int32_t z, y, x;   /* voxel coordinate inside the volume passed in */
+  int32_t s;         /* index into the sigma ladder */
+  float resp;        /* -sigma^2 * LoG response at the peak */
+} mmb_cand;
+
+/* ROI-profile preprocessing keys (magmap/settings/roi_prof.py:72-84). */
+typedef struct mmb_preproc_params {
+  double clip_vmin;          /* lower percentile, 0-100                         */
+  double clip_vmax;          /* upper percentile, 0-100                         */
+  double max_thresh;         /* config.near_max[chl] * max_thresh_factor        */
+  double clip_min, clip_max; /* clip after stretching                           */
+  double unsharp_strength;   /* 0 disables the sigma=8 unsharp mask             */
+  double erosion_threshold;  /* 0 disables; erode when block mean exceeds this  */
+} mmb_preproc_params;
+
+int mmb_version(void);
+const char* mmb_last_error(void);
+
+/* ---- img_as_float ---------------------------------------------------------
+ * Replaces skimage.util.img_as_float inside blob_log (reference call site
+ * magmap/cv/detector.py:931): out = in * scale, element strides given per axis
+ * so a channel of a channel-last (z,y,x,c) array can be read in place.        */
+int mmb_to_float(const void* in, int dtype, const int64_t in_strides[3],
+                 int Z, int Y, int X, float* out, int64_t pitch, double scale,
+                 void* stream);
+
+/* ---- saturate_roi + denoise_roi per preprocessing block --------------------
+ * Replaces the loop at magmap/cv/stack_detect.py:122-150 that calls
+ * plot_3d.saturate_roi (plot_3d.py:55-111) and plot_3d.denoise_roi
+ * (plot_3d.py:114-172) on every (bz,by,bx) block anchored at the chunk origin:
+ * exact np.percentile (linear) -> stretch -> clip -> sigma=8 'nearest' unsharp
+ * mask -> octahedron(1) erosion when the stretched block mean > threshold.
+ * One CTA per block.  Blocks larger than 32 voxels on any side: UNSUPPORTED.  */
+int mmb_preprocess_blocks(const void* in, int dtype, const int64_t in_strides[3],
+                          int Z, int Y, int X, int bz, int by, int bx,
+                          const mmb_preproc_params* p, float* out, int64_t pitch,
+                          void* stream);
+
+/* ---- one scale of the LoG cube ---------------------------------------------
+ * Replaces `-scipy.ndimage.gaussian_laplace(img, sigma) * sigma**2`
+ * (skimage blob_log, reached from magmap/cv/detector.py:931): truncate=4,
+ * radius=int(4*sigma+0.5), mode='reflect' on all faces of the volume given.
+ * `work` must hold mmb_log_work_bytes() bytes; `out` may not alias `in`.      */
+int64_t mmb_log_work_bytes(int Z, int Y, int64_t pitch);
+int mmb_log_scale(const float* in, float* out, void* work, int Z, int Y, int X,
+                  int64_t pitch, double sigma, void* stream);
+
+/* Separable Gaussian-derivative passes exposed one by one for parity tests and
+ * per-pass roofline measurement.  axis: 0=z 1=y 2=x.  mode: 0 = one input ->
+ * (g*in0, h*in0); 1 = (in0,in1) -> (g*in0, h*in0 + g*in1); 2 = (in0,in1) ->
+ * scale*(h*in0 + g*in1) in out0.  g = sampled Gaussian, h = its second
+ * derivative, as scipy.ndimage._filters._gaussian_kernel1d builds them.       */
+int mmb_log_pass(const float* in0, const float* in1, float* out0, float* out1,
+                 int Z, int Y, int X, int64_t pitch, int axis, int mode,
+                 double sigma, double scale, void* stream);
+
+/* ---- 4-D local maxima + threshold ------------------------------------------
+ * Replaces skimage.feature.peak_local_max(cube, threshold_abs=thr,
+ * footprint=ones((3,3,3,3)), exclude_border=False) for scale `s` given the
+ * neighbouring scales (NULL where absent = 'nearest' at the ends of the scale
+ * axis).  Emits voxels with z in [z_lo, z_hi).  *counter is a device int that
+ * the caller zeroes; it counts every peak even beyond `capacity`.             */
+int mmb_localmax_compact(const float* prev, const float* cur, const float* next,
+                         int Z, int Y, int X, int64_t pitch, int s, float thr,
+                         int z_lo, int z_hi, mmb_cand* out, int capacity,
+                         int* counter, void* stream);
+
+/* ---- within-volume overlap pruning ------------------------------------------
+ * Replaces skimage.feature.blob._prune_blobs (sphere-overlap test on
+ * [z,y,x,sigma] rows) with the order-independent resolution described in
+ * DESIGN.md.  keep[i] = 1 if candidate i survives.  Synchronous on `stream`.
+ * Candidate order matters only for ties: on equal sigma the candidate with the
+ * higher response (then lower C-order index) is the one removed, as in
+ * scikit-image.  `dims` = {Y, X} of the volume the coordinates refer to (for
+ * the tie order), `num_sigma` = ladder length.                                */
+int mmb_prune_within(const mmb_cand* cand, int n, const double* sigmas,
+                     int num_sigma, double overlap, int Y, int X,
+                     uint8_t* keep, void* stream);
+
+/* ---- seam matching ------------------------------------------------------------
+ * Replaces detector._find_close_blobs inside remove_close_blobs
+ * (magmap/cv/detector.py:1000-1085): box test |d| <= tol per axis between
+ * master and check rows (int32 z,y,x triples).  check_hit[j] = 1 if any master
+ * matches; master_last[i] = largest matching check index or -1 (the match that
+ * wins the reference's repeated fancy-index assignment).                     */
+int mmb_prune_seams(const int32_t* master_zyx, int n_master,
+                    const int32_t* check_zyx, int n_check, const int32_t tol[3],
+                    int32_t* master_last, uint8_t* check_hit, void* stream);
+
+/* ---- fused per-chunk driver -----------------------------------------------------
+ * Replaces StackDetector.detect_sub_roi's arithmetic
+ * (magmap/cv/stack_detect.py:122-158): optional block preprocessing (pre !=
+ * NULL, else plain img_as_float with `scale`), the num_sigma LoG scales kept in
+ * a 3-deep ring, local maxima, overlap pruning.  Survivors are compacted to
+ * the front of `cand`; *n_out (host) receives their count and *n_peaks (host,
+ * may be NULL) the number of local maxima before pruning.  Synchronous.
+ * `work` must hold mmb_detect_work_bytes() bytes.                             */
+int64_t mmb_detect_work_bytes(int Z, int Y, int64_t pitch, int capacity);
+int mmb_detect_chunk(const void* in, int dtype, const int64_t in_strides[3],
+                     int Z, int Y, int X, int64_t pitch, double scale,
+                     const mmb_preproc_params* pre, int bz, int by, int bx,
+                     const double* sigmas, int num_sigma, double threshold,
+                     double overlap, int z_lo, int z_hi, void* work,
+                     mmb_cand* cand, int capacity, int* n_out, int* n_peaks,
+                     void* stream);
+
+/* number of kernels this library has launched in this process (bench.py's
+ * gpu_launches).                                                              */
+int64_t mmb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMB200_H */

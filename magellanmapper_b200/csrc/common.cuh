@@ -1,0 +1,67 @@
+// Shared helpers for the mmb200 CUDA library (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include "../../include/mmb200.h"
+
+namespace mmb {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+#define MMB_CHECK_CUDA(expr)                                                   \
+  do {                                                                         \
+    cudaError_t _e = (expr);                                                   \
+    if (_e != cudaSuccess) {                                                   \
+      mmb::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr,              \
+                     cudaGetErrorString(_e));                                  \
+      return MMB_ERR_CUDA;                                                     \
+    }                                                                          \
+  } while (0)
+
+#define MMB_CHECK_LAUNCH()                                                     \
+  do {                                                                         \
+    mmb::g_launches.fetch_add(1, std::memory_order_relaxed);                   \
+    MMB_CHECK_CUDA(cudaGetLastError());                                        \
+  } while (0)
+
+#define MMB_REQUIRE(cond, msg)                                                 \
+  do {                                                                         \
+    if (!(cond)) {                                                             \
+      mmb::set_error("%s:%d invalid argument: %s", __FILE__, __LINE__, msg);   \
+      return MMB_ERR_INVALID;                                                  \
+    }                                                                          \
+  } while (0)
+
+// scipy.ndimage 'reflect' (d c b a | a b c d | d c b a): whole-sample symmetric
+// extension with period 2n, valid for any distance outside the array.
+__host__ __device__ __forceinline__ int reflect_index(int p, int n) {
+  if (p >= 0 && p < n) return p;
+  int m = 2 * n;
+  p %= m;
+  if (p < 0) p += m;
+  return p < n ? p : m - 1 - p;
+}
+
+__host__ __device__ __forceinline__ int clamp_index(int p, int n) {
+  return p < 0 ? 0 : (p >= n ? n - 1 : p);
+}
+
+constexpr int kMaxRadius = 64;   // templated fast paths cover radius <= 64
+
+// Sampled Gaussian g[k] and second derivative h[k] for k = 0..r (both even),
+// scipy.ndimage._filters._gaussian_kernel1d with truncate = 4.0.
+struct LogWeights {
+  float g[kMaxRadius + 1];
+  float h[kMaxRadius + 1];
+};
+
+int gaussian_radius(double sigma);
+// fills w (zero beyond r); returns r or -1 if r > kMaxRadius
+int make_log_weights(double sigma, LogWeights* w);
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace mmb

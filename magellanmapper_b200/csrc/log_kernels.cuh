@@ -1,0 +1,190 @@
+// Separable Gaussian / Gaussian-second-derivative passes of the LoG cube.
+//
+// scipy.ndimage.gaussian_laplace(img, s) = sum over axes a of
+// gaussian_filter(img, s, order=2 on a, 0 elsewhere) - nine correlate1d sweeps
+// per scale (scipy/ndimage/_filters.py:1120-1139, 845-848).  With g the sampled
+// Gaussian and h its second derivative the same sum factors into seven 1-D
+// convolutions over three sweeps:
+//     x:  A = g*I          B = h*I                 (MODE_FIRST)
+//     y:  C = g*A          D = h*A + g*B           (MODE_MID)
+//     z:  out = scale * (h*C + g*D)                (MODE_LAST, scale = -sigma^2)
+// Each sweep is FP32-issue bound (about 2r+1 FMAs per convolution per voxel,
+// r = 12..20 for sigma 3..5), so every thread owns NB consecutive outputs along
+// the filtered axis and streams NB+2r inputs through registers once, scattering
+// each into the accumulators it touches.  Tap weights are read from the kernel
+// parameter block, i.e. constant-bank operands of the FMAs.
+#pragma once
+#include "common.cuh"
+
+namespace mmb {
+
+enum { MODE_FIRST = 0, MODE_MID = 1, MODE_LAST = 2 };
+
+// Convolution along a strided axis (y or z).  The volume is viewed as
+// [outer][n_axis][inner] with `inner` contiguous: (Z, Y, pitch) for the y sweep,
+// (1, Z, Y*pitch) for the z sweep.  Thread = one inner position, NB outputs.
+// grid = (ceil(inner / threads), ceil(n_axis / NB), outer).
+template <int R, int MODE, int NB, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+conv_strided_kernel(const float* __restrict__ in0, const float* __restrict__ in1,
+                    float* __restrict__ out0, float* __restrict__ out1, int n_axis,
+                    int64_t inner, int64_t outer_stride,
+                    const __grid_constant__ LogWeights w, float scale) {
+  constexpr int NIN = NB + 2 * R;
+  __shared__ int64_t s_off[NIN];
+  const int a0 = blockIdx.y * NB;
+  for (int k = threadIdx.x; k < NIN; k += THREADS)
+    s_off[k] = (int64_t)reflect_index(a0 - R + k, n_axis) * inner;
+  __syncthreads();
+  const int64_t xi = (int64_t)blockIdx.x * THREADS + threadIdx.x;
+  if (xi >= inner) return;
+  const int64_t base = (int64_t)blockIdx.z * outer_stride + xi;
+  const float* p0 = in0 + base;
+  const float* p1 = (MODE == MODE_FIRST) ? nullptr : in1 + base;
+
+  float acc0[NB], acc1[NB];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+
+#pragma unroll
+  for (int k = 0; k < NIN; ++k) {
+    const int64_t off = s_off[k];
+    const float v0 = __ldg(p0 + off);
+    const float v1 = (MODE == MODE_FIRST) ? 0.f : __ldg(p1 + off);
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int t = k - j;
+      if (t >= 0 && t <= 2 * R) {
+        const int wi = t >= R ? t - R : R - t;
+        if (MODE == MODE_FIRST) {
+          acc0[j] = fmaf(w.g[wi], v0, acc0[j]);
+          acc1[j] = fmaf(w.h[wi], v0, acc1[j]);
+        } else if (MODE == MODE_MID) {
+          acc0[j] = fmaf(w.g[wi], v0, acc0[j]);
+          acc1[j] = fmaf(w.h[wi], v0, acc1[j]);
+          acc1[j] = fmaf(w.g[wi], v1, acc1[j]);
+        } else {
+          acc0[j] = fmaf(w.h[wi], v0, acc0[j]);
+          acc0[j] = fmaf(w.g[wi], v1, acc0[j]);
+        }
+      }
+    }
+  }
+
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    const int a = a0 + j;
+    if (a < n_axis) {
+      const int64_t o = base + (int64_t)a * inner;
+      if (MODE == MODE_LAST) {
+        out0[o] = acc0[j] * scale;
+      } else {
+        out0[o] = acc0[j];
+        out1[o] = acc1[j];
+      }
+    }
+  }
+}
+
+// First sweep along the contiguous x axis.  A CTA owns 32 rows x (NB*NSEG)
+// outputs; the input tile (with its 2R halo) is staged in shared memory with an
+// odd row pitch, so "lane = row" accesses are bank-conflict free; thread
+// (lane = row, warp = segment) owns NB consecutive x outputs.  Results go back
+// through the same shared tile so global stores are coalesced along x.
+// grid = (ceil(nrows / 32), ceil(X / (NB*NSEG))).
+template <int R, int NB, int NSEG>
+__global__ void __launch_bounds__(32 * NSEG)
+conv_x_first_kernel(const float* __restrict__ in, float* __restrict__ outA,
+                    float* __restrict__ outB, int64_t nrows, int X, int64_t pitch,
+                    const __grid_constant__ LogWeights w) {
+  constexpr int WT = NB * NSEG;
+  constexpr int WIN = WT + 2 * R;
+  constexpr int SP = WIN | 1;       // odd pitch for the input tile
+  constexpr int OP = WT | 1;        // odd pitch for the output staging tile
+  __shared__ float s[32 * SP];
+  const int lane = threadIdx.x & 31;
+  const int seg = threadIdx.x >> 5;
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int x0 = blockIdx.y * WT;
+  const bool x_interior = (x0 - R >= 0) && (x0 + WT + R <= X);
+
+  for (int rr = seg; rr < 32; rr += NSEG) {
+    const int64_t row = r0 + rr;
+    const float* src = in + row * pitch;
+    for (int c = lane; c < WIN; c += 32) {
+      float v = 0.f;
+      if (row < nrows) {
+        const int x = x_interior ? (x0 - R + c) : reflect_index(x0 - R + c, X);
+        v = __ldg(src + x);
+      }
+      s[rr * SP + c] = v;
+    }
+  }
+  __syncthreads();
+
+  float accA[NB], accB[NB];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) { accA[j] = 0.f; accB[j] = 0.f; }
+  const float* srow = s + lane * SP + seg * NB;
+#pragma unroll
+  for (int k = 0; k < NB + 2 * R; ++k) {
+    const float v = srow[k];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int t = k - j;
+      if (t >= 0 && t <= 2 * R) {
+        const int wi = t >= R ? t - R : R - t;
+        accA[j] = fmaf(w.g[wi], v, accA[j]);
+        accB[j] = fmaf(w.h[wi], v, accB[j]);
+      }
+    }
+  }
+  __syncthreads();
+
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    float* dst = pass == 0 ? outA : outB;
+#pragma unroll
+    for (int j = 0; j < NB; ++j)
+      s[lane * OP + seg * NB + j] = pass == 0 ? accA[j] : accB[j];
+    __syncthreads();
+    for (int rr = seg; rr < 32; rr += NSEG) {
+      const int64_t row = r0 + rr;
+      if (row < nrows) {
+        for (int c = lane; c < WT; c += 32) {
+          const int x = x0 + c;
+          if (x < X) dst[row * pitch + x] = s[rr * OP + c];
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Slow generic fallbacks for radii above kMaxRadius (weights in global memory).
+__global__ void conv_generic_kernel(const float* __restrict__ in0,
+                                    const float* __restrict__ in1,
+                                    float* __restrict__ out0, float* __restrict__ out1,
+                                    int Z, int Y, int X, int64_t pitch, int axis, int mode,
+                                    const float* __restrict__ g, const float* __restrict__ h,
+                                    int r, float scale);
+
+int launch_strided(int mode, int r, const float* in0, const float* in1, float* out0,
+                   float* out1, int n_axis, int64_t inner, int64_t outer,
+                   const LogWeights& w, float scale, cudaStream_t st);
+int launch_strided_m0(int r, const float*, const float*, float*, float*, int, int64_t,
+                      int64_t, const LogWeights&, float, cudaStream_t);
+int launch_strided_m1(int r, const float*, const float*, float*, float*, int, int64_t,
+                      int64_t, const LogWeights&, float, cudaStream_t);
+int launch_strided_m2(int r, const float*, const float*, float*, float*, int, int64_t,
+                      int64_t, const LogWeights&, float, cudaStream_t);
+int launch_x_first(int r, const float* in, float* outA, float* outB, int64_t nrows, int X,
+                   int64_t pitch, const LogWeights& w, cudaStream_t st);
+
+// Radius buckets with a compiled kernel; a request is served by the smallest
+// bucket >= r (taps beyond r carry zero weight).
+#define MMB_RADIUS_BUCKETS(X) \
+  X(2) X(4) X(6) X(8) X(10) X(12) X(13) X(14) X(15) X(16) X(17) X(18) X(19) X(20) \
+  X(24) X(32) X(48) X(64)
+
+}  // namespace mmb

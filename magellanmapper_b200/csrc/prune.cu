@@ -1,0 +1,245 @@
+// Overlap pruning inside a volume (_prune_blobs) and seam matching across chunks
+// (remove_close_blobs).
+//
+// _prune_blobs walks the pairs closer than 2*sigma_max*sqrt(3) and, when the
+// smaller sphere (radius sigma*sqrt(3)) has more than `overlap` of its volume
+// inside the larger one, zeroes the smaller-sigma blob (on equal sigma the one
+// listed first = stronger response).  A zeroed blob never removes another one,
+// which makes the sequential result depend on the iteration order of a Python
+// set.  Here the pair tests produce a kill graph (killer -> victim, acyclic) and
+// the graph is resolved order-independently: a blob survives iff none of its
+// killers survives.  DESIGN.md states where this can differ from one particular
+// scikit-image run (chains only) and how the tests bound it.
+#include <math.h>
+#include <vector>
+#include "common.cuh"
+
+namespace mmb {
+
+__device__ __forceinline__ bool listed_first(float ra, long long la, float rb, long long lb) {
+  // order of peak_local_max: descending response, ties in C order
+  return ra > rb || (ra == rb && la < lb);
+}
+
+// sphere-overlap fraction as skimage.feature.blob._blob_overlap computes it in
+// float64: same operation order, no FMA contraction
+__device__ double overlap_f64(const mmb_cand& a, const mmb_cand& b, double s1, double s2) {
+  const double root = sqrt(3.0);
+  double big, r1, r2;
+  if (s1 > s2) { big = s1; r1 = 1.0; r2 = __ddiv_rn(s2, s1); }
+  else         { big = s2; r1 = __ddiv_rn(s1, s2); r2 = 1.0; }
+  const double den = __dmul_rn(big, root);
+  const double ez = __dadd_rn(__ddiv_rn((double)b.z, den), -__ddiv_rn((double)a.z, den));
+  const double ey = __dadd_rn(__ddiv_rn((double)b.y, den), -__ddiv_rn((double)a.y, den));
+  const double ex = __dadd_rn(__ddiv_rn((double)b.x, den), -__ddiv_rn((double)a.x, den));
+  const double ss = __dadd_rn(__dadd_rn(__dmul_rn(ez, ez), __dmul_rn(ey, ey)), __dmul_rn(ex, ex));
+  const double d = __dsqrt_rn(ss);
+  const double rs = __dadd_rn(r1, r2);
+  if (d > rs) return 0.0;
+  if (d <= fabs(__dadd_rn(r1, -r2))) return 1.0;
+  const double pi = 3.141592653589793;
+  // vol = pi/(12 d) * (r1+r2-d)^2 * (d^2 + 2 d (r1+r2) - 3 (r1^2 + r2^2) + 6 r1 r2)
+  const double t0 = __ddiv_rn(pi, __dmul_rn(12.0, d));
+  const double t1 = __dadd_rn(rs, -d);
+  const double t1s = __dmul_rn(t1, t1);
+  double poly = __dadd_rn(__dmul_rn(d, d), __dmul_rn(__dmul_rn(2.0, d), rs));
+  poly = __dadd_rn(poly, -__dmul_rn(3.0, __dadd_rn(__dmul_rn(r1, r1), __dmul_rn(r2, r2))));
+  poly = __dadd_rn(poly, __dmul_rn(__dmul_rn(6.0, r1), r2));
+  const double vol = __dmul_rn(__dmul_rn(t0, t1s), poly);
+  const double m = r1 < r2 ? r1 : r2;
+  const double small = __dmul_rn(__dmul_rn(__ddiv_rn(4.0, 3.0), pi), __dmul_rn(__dmul_rn(m, m), m));
+  return __ddiv_rn(vol, small);
+}
+
+constexpr int kTile = 256;
+
+// all pairs i < j, tile of j staged in shared memory; emits (killer, victim)
+__global__ void __launch_bounds__(kTile)
+prune_edges_kernel(const mmb_cand* __restrict__ cand, int n, const double* __restrict__ sigmas,
+                   int num_sigma, double overlap, int Y, int X, int2* __restrict__ edges,
+                   int edge_cap, int* __restrict__ edge_count) {
+  __shared__ mmb_cand tile[kTile];
+  const int i = blockIdx.x * kTile + threadIdx.x;
+  mmb_cand me;
+  me.z = me.y = me.x = 0; me.s = 0; me.resp = 0.f;
+  double my_sigma = 0.0;
+  if (i < n) { me = cand[i]; my_sigma = sigmas[me.s]; }
+  const double smax = sigmas[num_sigma - 1] > sigmas[0] ? sigmas[num_sigma - 1] : sigmas[0];
+  // spheres can only touch when |d| <= (s1+s2)*sqrt(3) <= 2*smax*sqrt(3)
+  const float cut = (float)(2.0 * smax * 1.7320508075688772) + 1.0f;
+  const float cut2 = cut * cut;
+  // tiles with j > i only: start at this block's own tile
+  for (int j0 = blockIdx.x * kTile; j0 < n; j0 += kTile) {
+    __syncthreads();
+    const int jl = j0 + threadIdx.x;
+    if (jl < n) tile[threadIdx.x] = cand[jl];
+    __syncthreads();
+    if (i >= n) continue;
+    const int cnt = n - j0 < kTile ? n - j0 : kTile;
+    for (int t = 0; t < cnt; ++t) {
+      const int j = j0 + t;
+      if (j <= i) continue;
+      const mmb_cand o = tile[t];
+      const float dz = (float)(o.z - me.z);
+      if (fabsf(dz) > cut) continue;
+      const float dy = (float)(o.y - me.y), dx = (float)(o.x - me.x);
+      if (dz * dz + dy * dy + dx * dx > cut2) continue;
+      const double so = sigmas[o.s];
+      if (overlap_f64(me, o, my_sigma, so) > overlap) {
+        int killer, victim;
+        if (my_sigma > so) { killer = i; victim = j; }
+        else if (so > my_sigma) { killer = j; victim = i; }
+        else {
+          const long long li = (((long long)me.z * Y + me.y) * X + me.x) * num_sigma + me.s;
+          const long long lj = (((long long)o.z * Y + o.y) * X + o.x) * num_sigma + o.s;
+          // equal sigma: the blob listed first by peak_local_max is removed
+          if (listed_first(me.resp, li, o.resp, lj)) { victim = i; killer = j; }
+          else { victim = j; killer = i; }
+        }
+        const int e = atomicAdd(edge_count, 1);
+        if (e < edge_cap) edges[e] = make_int2(killer, victim);
+      }
+    }
+  }
+}
+
+// single-CTA fixed point over the kill graph. state: 0 unknown, 1 alive, 2 dead
+__global__ void __launch_bounds__(1024)
+prune_resolve_kernel(int n, const int2* __restrict__ edges, int n_edges,
+                     unsigned char* __restrict__ state, unsigned char* __restrict__ mark,
+                     unsigned char* __restrict__ keep) {
+  __shared__ int remaining;
+  for (int v = threadIdx.x; v < n; v += blockDim.x) state[v] = 0;
+  __syncthreads();
+  while (true) {
+    for (int v = threadIdx.x; v < n; v += blockDim.x) mark[v] = 0;
+    if (threadIdx.x == 0) remaining = 0;
+    __syncthreads();
+    for (int e = threadIdx.x; e < n_edges; e += blockDim.x) {
+      const int2 kv = edges[e];
+      if (state[kv.y] == 0) {
+        const unsigned char sk = state[kv.x];
+        if (sk == 1) atomicOr((unsigned int*)(mark + (kv.y & ~3)), 1u << (8 * (kv.y & 3)));
+        else if (sk == 0) atomicOr((unsigned int*)(mark + (kv.y & ~3)), 2u << (8 * (kv.y & 3)));
+      }
+    }
+    __syncthreads();
+    int mine = 0;
+    for (int v = threadIdx.x; v < n; v += blockDim.x) {
+      if (state[v] == 0) {
+        const unsigned char m = mark[v];
+        if (m & 1) state[v] = 2;
+        else if (!(m & 2)) state[v] = 1;
+        else ++mine;
+      }
+    }
+    if (mine) atomicAdd(&remaining, mine);
+    __syncthreads();
+    const int r = remaining;
+    __syncthreads();
+    if (r == 0) break;
+  }
+  for (int v = threadIdx.x; v < n; v += blockDim.x) keep[v] = state[v] == 1 ? 1 : 0;
+}
+
+int prune_within_impl(const mmb_cand* cand, int n, const double* sigmas_host, int num_sigma,
+                      double overlap, int Y, int X, uint8_t* keep, cudaStream_t st) {
+  if (n == 0) return MMB_OK;
+  double* d_sig = nullptr;
+  int* d_count = nullptr;
+  int2* d_edges = nullptr;
+  unsigned char* d_state = nullptr;
+  const int64_t npad = (n + 3) / 4 * 4 + 4;
+  MMB_CHECK_CUDA(cudaMallocAsync((void**)&d_sig, num_sigma * sizeof(double), st));
+  MMB_CHECK_CUDA(cudaMallocAsync((void**)&d_count, sizeof(int), st));
+  MMB_CHECK_CUDA(cudaMallocAsync((void**)&d_state, 2 * npad, st));
+  MMB_CHECK_CUDA(cudaMemcpyAsync(d_sig, sigmas_host, num_sigma * sizeof(double),
+                                 cudaMemcpyHostToDevice, st));
+  int edge_cap = 4 * n + 4096;
+  int n_edges = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    MMB_CHECK_CUDA(cudaMallocAsync((void**)&d_edges, (size_t)edge_cap * sizeof(int2), st));
+    MMB_CHECK_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), st));
+    prune_edges_kernel<<<(unsigned)cdiv(n, kTile), kTile, 0, st>>>(
+        cand, n, d_sig, num_sigma, overlap, Y, X, d_edges, edge_cap, d_count);
+    MMB_CHECK_LAUNCH();
+    MMB_CHECK_CUDA(cudaMemcpyAsync(&n_edges, d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    MMB_CHECK_CUDA(cudaStreamSynchronize(st));
+    if (n_edges <= edge_cap) break;
+    MMB_CHECK_CUDA(cudaFreeAsync(d_edges, st));
+    d_edges = nullptr;
+    edge_cap = n_edges;
+  }
+  if (n_edges > edge_cap) {
+    set_error("kill-edge buffer overflow (%d > %d)", n_edges, edge_cap);
+    return MMB_ERR_OVERFLOW;
+  }
+  prune_resolve_kernel<<<1, 1024, 0, st>>>(n, d_edges, n_edges, d_state, d_state + npad, keep);
+  MMB_CHECK_LAUNCH();
+  MMB_CHECK_CUDA(cudaFreeAsync(d_edges, st));
+  MMB_CHECK_CUDA(cudaFreeAsync(d_state, st));
+  MMB_CHECK_CUDA(cudaFreeAsync(d_count, st));
+  MMB_CHECK_CUDA(cudaFreeAsync(d_sig, st));
+  MMB_CHECK_CUDA(cudaStreamSynchronize(st));
+  return MMB_OK;
+}
+
+// ---- seam matching -----------------------------------------------------------
+
+__global__ void __launch_bounds__(kTile)
+seam_match_kernel(const int32_t* __restrict__ master, int nm, const int32_t* __restrict__ check,
+                  int nc, int tz, int ty, int tx, int32_t* __restrict__ master_last,
+                  unsigned char* __restrict__ check_hit) {
+  __shared__ int32_t tile[kTile * 3];
+  const int i = blockIdx.x * kTile + threadIdx.x;
+  int mz = 0, my = 0, mx = 0;
+  if (i < nm) { mz = master[3 * i]; my = master[3 * i + 1]; mx = master[3 * i + 2]; }
+  int last = -1;
+  for (int j0 = 0; j0 < nc; j0 += kTile) {
+    __syncthreads();
+    const int cnt = nc - j0 < kTile ? nc - j0 : kTile;
+    for (int t = threadIdx.x; t < cnt * 3; t += kTile) tile[t] = check[3 * j0 + t];
+    __syncthreads();
+    if (i >= nm) continue;
+    for (int t = 0; t < cnt; ++t) {
+      const int dz = abs(tile[3 * t] - mz), dy = abs(tile[3 * t + 1] - my),
+                dx = abs(tile[3 * t + 2] - mx);
+      if (dz <= tz && dy <= ty && dx <= tx) {
+        last = j0 + t;            // ascending j: the last hit is the largest index
+        check_hit[j0 + t] = 1;
+      }
+    }
+  }
+  if (i < nm) master_last[i] = last;
+}
+
+int prune_seams_impl(const int32_t* master, int nm, const int32_t* check, int nc,
+                     const int32_t tol[3], int32_t* master_last, uint8_t* check_hit,
+                     cudaStream_t st) {
+  if (nc > 0) MMB_CHECK_CUDA(cudaMemsetAsync(check_hit, 0, nc, st));
+  if (nm == 0) return MMB_OK;
+  seam_match_kernel<<<(unsigned)cdiv(nm, kTile), kTile, 0, st>>>(
+      master, nm, check, nc, tol[0], tol[1], tol[2], master_last, check_hit);
+  MMB_CHECK_LAUNCH();
+  return MMB_OK;
+}
+
+}  // namespace mmb
+
+extern "C" int mmb_prune_within(const mmb_cand* cand, int n, const double* sigmas, int num_sigma,
+                                double overlap, int Y, int X, uint8_t* keep, void* stream) {
+  MMB_REQUIRE(n >= 0 && num_sigma > 0 && sigmas, "bad arguments");
+  MMB_REQUIRE(n == 0 || (cand && keep), "null buffer");
+  return mmb::prune_within_impl(cand, n, sigmas, num_sigma, overlap, Y, X, keep,
+                                (cudaStream_t)stream);
+}
+
+extern "C" int mmb_prune_seams(const int32_t* master_zyx, int n_master, const int32_t* check_zyx,
+                               int n_check, const int32_t tol[3], int32_t* master_last,
+                               uint8_t* check_hit, void* stream) {
+  MMB_REQUIRE(n_master >= 0 && n_check >= 0 && tol, "bad arguments");
+  MMB_REQUIRE(n_master == 0 || (master_zyx && master_last), "null master buffer");
+  MMB_REQUIRE(n_check == 0 || (check_zyx && check_hit), "null check buffer");
+  return mmb::prune_seams_impl(master_zyx, n_master, check_zyx, n_check, tol, master_last,
+                               check_hit, (cudaStream_t)stream);
+}

@@ -1,0 +1,237 @@
+"""Thin torch-tensor wrappers over the C ABI (``include/mmb200.h``).
+
+PyTorch is plumbing only: device allocations, streams, host<->device copies.
+Every function here ends in a call into ``libmmb200.so``; none has a CPU path.
+
+Float volumes are ``(Z, Y, pitch)`` float32 CUDA tensors whose rows are padded
+to a multiple of 32 elements; the logical width ``X`` travels alongside.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import MmbCand, MmbPreprocParams
+
+_NP2MMB = {np.dtype(np.uint8): _lib.MMB_U8, np.dtype(np.uint16): _lib.MMB_U16,
+           np.dtype(np.float32): _lib.MMB_F32, np.dtype(np.float64): _lib.MMB_F64}
+_T2MMB = {torch.uint8: _lib.MMB_U8, torch.uint16: _lib.MMB_U16, torch.int16: _lib.MMB_U16,
+          torch.float32: _lib.MMB_F32, torch.float64: _lib.MMB_F64}
+
+CAND_DTYPE = np.dtype([("z", "<i4"), ("y", "<i4"), ("x", "<i4"), ("s", "<i4"), ("resp", "<f4")])
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("magellanmapper_b200 needs a CUDA device; there is no CPU fallback")
+    _lib.load()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def pitch_for(x: int) -> int:
+    return (int(x) + 31) // 32 * 32
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def new_volume(Z: int, Y: int, X: int, device=None) -> torch.Tensor:
+    return torch.zeros((Z, Y, pitch_for(X)), dtype=torch.float32, device=device or require_cuda())
+
+
+@dataclass
+class Source:
+    """A 3-D (z, y, x) view of device memory in its native dtype."""
+    tensor: torch.Tensor          # keeps the storage alive
+    ptr: int
+    dtype: int
+    strides: Tuple[int, int, int]
+    shape: Tuple[int, int, int]
+
+
+def as_source(arr, channel: Optional[int] = None, device=None) -> Source:
+    """Upload (if needed) and describe one channel of a (z,y,x[,c]) array.
+
+    numpy uint16 has no full torch support, so it is moved as int16 bits; the
+    library is told the true dtype.
+    """
+    device = device or require_cuda()
+    if isinstance(arr, np.ndarray):
+        dt = _NP2MMB.get(arr.dtype)
+        if dt is None:
+            # rare dtypes (int32, float16, bool...) go through float32 on the host side of the copy
+            arr = arr.astype(np.float32)
+            dt = _lib.MMB_F32
+        a = np.ascontiguousarray(arr)
+        if a.dtype == np.uint16:
+            t = torch.from_numpy(a.view(np.int16))
+        else:
+            t = torch.from_numpy(a)
+        t = t.to(device, non_blocking=True)
+    elif isinstance(arr, torch.Tensor):
+        dt = _T2MMB.get(arr.dtype)
+        if dt is None:
+            raise TypeError(f"unsupported tensor dtype {arr.dtype}")
+        t = arr if arr.is_cuda else arr.to(device, non_blocking=True)
+    else:
+        raise TypeError(f"expected numpy array or torch tensor, got {type(arr)}")
+    if t.dim() == 4:
+        c = 0 if channel is None else int(channel)
+        view = t[..., c]
+    elif t.dim() == 3:
+        view = t
+    else:
+        raise ValueError(f"expected a (z,y,x) or (z,y,x,c) array, got {tuple(t.shape)}")
+    return Source(t, view.data_ptr(), dt, tuple(int(s) for s in view.stride()),
+                  tuple(int(s) for s in view.shape))
+
+
+def to_float(src: Source, scale: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    Z, Y, X = src.shape
+    out = out if out is not None else new_volume(Z, Y, X, src.tensor.device)
+    _lib.check(lib.mmb_to_float(C.c_void_p(src.ptr), src.dtype, _lib._I64x3(*src.strides), Z, Y, X,
+                                _ptr(out), out.shape[2], float(scale), _stream()))
+    return out
+
+
+def preprocess_blocks(src: Source, block_shape: Sequence[int], params: MmbPreprocParams,
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    Z, Y, X = src.shape
+    out = out if out is not None else new_volume(Z, Y, X, src.tensor.device)
+    bz, by, bx = (int(b) for b in block_shape)
+    _lib.check(lib.mmb_preprocess_blocks(
+        C.c_void_p(src.ptr), src.dtype, _lib._I64x3(*src.strides), Z, Y, X, bz, by, bx,
+        C.byref(params), _ptr(out), out.shape[2], _stream()))
+    return out
+
+
+def log_pass(in0, in1, X: int, axis: int, mode: int, sigma: float, scale: float = 1.0):
+    """One separable sweep (see ``mmb_log_pass``); returns (out0, out1|None)."""
+    lib = _lib.load()
+    Z, Y, pitch = in0.shape
+    out0 = torch.zeros_like(in0)
+    out1 = torch.zeros_like(in0) if mode != 2 else None
+    _lib.check(lib.mmb_log_pass(_ptr(in0), _ptr(in1), _ptr(out0), _ptr(out1), Z, Y, X, pitch,
+                                axis, mode, float(sigma), float(scale), _stream()))
+    return out0, out1
+
+
+def log_scale(vol: torch.Tensor, X: int, sigma: float, out: Optional[torch.Tensor] = None,
+              work: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``-gaussian_laplace(vol, sigma) * sigma**2`` with scipy 'reflect' faces."""
+    lib = _lib.load()
+    Z, Y, pitch = vol.shape
+    out = out if out is not None else torch.zeros_like(vol)
+    if work is None:
+        work = torch.zeros(lib.mmb_log_work_bytes(Z, Y, pitch), dtype=torch.uint8,
+                           device=vol.device)
+    _lib.check(lib.mmb_log_scale(_ptr(vol), _ptr(out), _ptr(work), Z, Y, X, pitch, float(sigma),
+                                 _stream()))
+    return out
+
+
+def new_cand_buffer(capacity: int, device=None) -> torch.Tensor:
+    return torch.zeros((capacity, 5), dtype=torch.int32, device=device or require_cuda())
+
+
+def cands_to_numpy(buf: torch.Tensor, n: int) -> np.ndarray:
+    host = buf[:n].cpu().numpy()
+    return host.view(CAND_DTYPE).reshape(-1).copy()
+
+
+def cands_from_numpy(c: np.ndarray, device=None) -> torch.Tensor:
+    raw = np.ascontiguousarray(c.astype(CAND_DTYPE)).view(np.int32).reshape(-1, 5)
+    return torch.from_numpy(raw.copy()).to(device or require_cuda())
+
+
+def localmax(prev, cur, nxt, X: int, s: int, thr: float, cand: torch.Tensor,
+             counter: torch.Tensor, z_lo: int = 0, z_hi: Optional[int] = None) -> None:
+    lib = _lib.load()
+    Z, Y, pitch = cur.shape
+    z_hi = Z if z_hi is None else z_hi
+    _lib.check(lib.mmb_localmax_compact(_ptr(prev), _ptr(cur), _ptr(nxt), Z, Y, X, pitch, int(s),
+                                        float(thr), int(z_lo), int(z_hi), _ptr(cand),
+                                        cand.shape[0], _ptr(counter), _stream()))
+
+
+def prune_within(cand: torch.Tensor, n: int, sigmas: Sequence[float], overlap: float, Y: int,
+                 X: int) -> torch.Tensor:
+    lib = _lib.load()
+    keep = torch.zeros(max(n, 1), dtype=torch.uint8, device=cand.device)
+    sig = (C.c_double * len(sigmas))(*[float(s) for s in sigmas])
+    _lib.check(lib.mmb_prune_within(_ptr(cand), int(n), sig, len(sigmas), float(overlap), int(Y),
+                                    int(X), _ptr(keep), _stream()))
+    return keep[:n]
+
+
+def prune_seams(master_zyx: torch.Tensor, check_zyx: torch.Tensor, tol: Sequence[int]):
+    """Box match of int32 (n,3) coordinate tensors; returns (master_last, check_hit)."""
+    lib = _lib.load()
+    nm, nc = master_zyx.shape[0], check_zyx.shape[0]
+    dev = master_zyx.device
+    master_last = torch.full((max(nm, 1),), -1, dtype=torch.int32, device=dev)
+    check_hit = torch.zeros(max(nc, 1), dtype=torch.uint8, device=dev)
+    _lib.check(lib.mmb_prune_seams(_ptr(master_zyx), nm, _ptr(check_zyx), nc,
+                                   _lib._I32x3(*[int(t) for t in tol]), _ptr(master_last),
+                                   _ptr(check_hit), _stream()))
+    return master_last[:nm], check_hit[:nc]
+
+
+class ChunkDetector:
+    """Reusable workspace around ``mmb_detect_chunk`` for chunks up to a
+    maximum shape (the workspace is the dominant allocation: eight float
+    volumes)."""
+
+    def __init__(self, max_shape: Sequence[int], capacity: Optional[int] = None, device=None):
+        self.lib = _lib.load()
+        self.device = device or require_cuda()
+        self.max_shape = tuple(int(s) for s in max_shape)
+        Z, Y, X = self.max_shape
+        nvox = Z * Y * X
+        self.capacity = int(capacity) if capacity else max(4096, nvox // 256)
+        self._alloc()
+
+    def _alloc(self):
+        Z, Y, X = self.max_shape
+        nbytes = self.lib.mmb_detect_work_bytes(Z, Y, pitch_for(X), self.capacity)
+        self.work = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        self.cand = new_cand_buffer(self.capacity, self.device)
+
+    def detect(self, src: Source, sigmas: Sequence[float], threshold: float, overlap: float,
+               scale: float = 1.0, pre: Optional[MmbPreprocParams] = None,
+               block_shape: Sequence[int] = (25, 25, 25), z_lo: int = 0,
+               z_hi: Optional[int] = None) -> Tuple[np.ndarray, int]:
+        """Returns ``(survivors as CAND_DTYPE records, number of local maxima)``."""
+        Z, Y, X = src.shape
+        if Z > self.max_shape[0] or Y > self.max_shape[1] or X > self.max_shape[2]:
+            raise ValueError(f"chunk {src.shape} exceeds workspace {self.max_shape}")
+        z_hi = Z if z_hi is None else z_hi
+        sig = (C.c_double * len(sigmas))(*[float(s) for s in sigmas])
+        bz, by, bx = (int(b) for b in block_shape)
+        while True:
+            n_out, n_peaks = C.c_int(0), C.c_int(0)
+            rc = self.lib.mmb_detect_chunk(
+                C.c_void_p(src.ptr), src.dtype, _lib._I64x3(*src.strides), Z, Y, X, pitch_for(X),
+                float(scale), C.byref(pre) if pre is not None else None, bz, by, bx, sig,
+                len(sigmas), float(threshold), float(overlap), int(z_lo), int(z_hi),
+                _ptr(self.work), _ptr(self.cand), self.capacity, C.byref(n_out),
+                C.byref(n_peaks), _stream())
+            if rc == _lib.MMB_ERR_OVERFLOW:
+                # counted exactly: grow once to the reported size and redo the chunk
+                self.capacity = int(n_out.value * 1.25) + 1024
+                self._alloc()
+                continue
+            _lib.check(rc)
+            return cands_to_numpy(self.cand, n_out.value), n_peaks.value
