@@ -54,10 +54,11 @@ preprocess_kernel(const T* __restrict__ in, PreGeom g, mmb_preproc_params p,
                   float* __restrict__ out) {
   constexpr int NVOX = NL * NL * NL;
   constexpr int NPT = (NVOX + kPreThreads - 1) / kPreThreads;
+  constexpr int NVOXP = (NVOX + 3) / 4 * 4;      // keeps M 16-byte aligned for float4 rows
   constexpr int NLP = (NL + 3) / 4 * 4;          // matrix row pitch (float4 rows)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* vals = reinterpret_cast<float*>(smem_raw);                 // NVOX
-  float* M = vals + NVOX;                                            // 3 * NL * NLP
+  float* M = vals + NVOXP;                                           // 3 * NL * NLP
   int* hist = reinterpret_cast<int*>(M + 3 * NL * NLP);              // 2 * 256
   __shared__ unsigned s_prefix[2];
   __shared__ int s_k[2];
@@ -347,7 +348,7 @@ template <typename T, int NL>
 static int launch_pre(const void* in, const PreGeom& g, const mmb_preproc_params& p,
                       const float* mats, int mat_pitch, float* out, cudaStream_t st) {
   constexpr int NLP = (NL + 3) / 4 * 4;
-  const size_t smem = (size_t)NL * NL * NL * 4 + (size_t)3 * NL * NLP * 4 + 512 * 4;
+  const size_t smem = (size_t)((NL * NL * NL + 3) / 4 * 4) * 4 + (size_t)3 * NL * NLP * 4 + 512 * 4;
   static bool configured = false;
   auto kern = preprocess_kernel<T, NL>;
   if (!configured) {
