@@ -1,0 +1,482 @@
+"""Blob detection on the GPU behind the ``magmap.cv.detector`` surface.
+
+Mirror of ``magmap/cv/detector.py``: the ``Blobs`` table container and its
+column schema (``:46-807``), ``calc_scaling_factor`` / ``calc_overlap``
+(``:810-841``), ``detect_blobs`` (``:874-957``), seam pruning
+``remove_close_blobs`` (``:1000-1085``) and the ROI filters
+(``:1210-1268``).  Same names, argument order and array layouts; the arithmetic
+(``skimage.feature.blob_log`` in the reference) runs in ``libmmb200.so``.
+"""
+from __future__ import annotations
+
+import math
+from enum import Enum
+from typing import Callable, Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from ..io import libmag, np_io
+from ..plot import plot_3d
+from ..settings import config
+
+#: blob confirmation flags
+CONFIRMATION: Dict[int, str] = {-1: "unverified", 0: "no", 1: "yes", 2: "maybe"}
+#: pixels of sub-ROI overlap per unit of scaling
+OVERLAP_FACTOR: int = 5
+
+_logger = config.logger.getChild(__name__)
+
+
+class Blobs:
+    """Blob table ``[[z, y, x, radius, confirmed, truth, channel, abs_z, abs_y,
+    abs_x, region], ...]`` plus archive metadata.
+
+    Column positions live in the CLASS attribute ``_col_inds`` and are rewritten
+    whenever ``cols`` is assigned (as in the reference, ``detector.py:116,
+    142-162``), so the class-level accessors always describe the most recently
+    configured table.
+    """
+
+    #: archive version (5: abs-coordinate columns removed from stored tables)
+    BLOBS_NP_VER: int = 5
+
+    class Keys(Enum):
+        VER = "ver"
+        BLOBS = "segments"
+        COLOCS = "colocs"
+        RESOLUTIONS = "resolutions"
+        BASENAME = "basename"
+        ROI_OFFSET = "offset"
+        ROI_SIZE = "roi_size"
+        COLS = "columns"
+
+    class Cols(Enum):
+        Z = "z"
+        Y = "y"
+        X = "x"
+        RADIUS = "radius"
+        CONFIRMED = "confirmed"
+        TRUTH = "truth"
+        CHANNEL = "channel"
+        ABS_Z = "abs_z"
+        ABS_Y = "abs_y"
+        ABS_X = "abs_x"
+        REGION = "region"
+
+    _col_inds: Dict["Blobs.Cols", Optional[int]] = {c: i for i, c in enumerate(Cols)}
+
+    def __init__(self, blobs=None, blob_matches=None, colocalizations=None, path=None,
+                 cols=None):
+        self.cols = cols
+        self.blobs = blobs
+        self.blob_matches = blob_matches
+        self.colocalizations = colocalizations
+        self.path = path
+        self.ver = self.BLOBS_NP_VER
+        self.roi_offset = None
+        self.roi_size = None
+        self.resolutions = None
+        self.basename = None
+        self.scaling = np.ones(3)
+
+    # -- schema -----------------------------------------------------------------
+    @property
+    def cols(self):
+        return self._cols
+
+    @cols.setter
+    def cols(self, cols):
+        self._cols = cols
+        if cols is None:
+            return
+        inds = {c: None for c in self.Cols}
+        for i, name in enumerate(cols):
+            try:
+                inds[self.Cols(name)] = i
+            except ValueError:
+                _logger.warning("%s is not a valid Blobs column, skipping", name)
+        Blobs._col_inds = inds
+
+    @property
+    def blobs(self):
+        return self._blobs
+
+    @blobs.setter
+    def blobs(self, blobs):
+        self._blobs = blobs
+        if blobs is not None and self.cols is None:
+            self.cols = [c.value for c in self.Cols][:blobs.shape[1]]
+
+    def format_blobs(self, channel=None) -> np.ndarray:
+        """Widen ``[z, y, x, radius, ...]`` to every column of ``Cols`` (new
+        columns = -1), copy relative into absolute coordinates and optionally
+        set the channel (detector.py:325-364)."""
+        n, have = self.blobs.shape
+        pad = np.full((n, len(self.Cols) - have), -1.0)
+        self.blobs = np.concatenate((self.blobs, pad), axis=1)
+        self.cols = [c.value for c in self.Cols]
+        self.blobs[:, self._get_abs_inds()] = self.blobs[:, self._get_rel_inds()]
+        if channel is not None:
+            self.set_blob_channel(self.blobs, channel)
+        return self.blobs
+
+    # -- archive ------------------------------------------------------------------
+    def load_blobs(self, path: Optional[str] = None) -> "Blobs":
+        """Read a ``*_blobs.npz`` archive (detector.py:185-267)."""
+        if path is not None:
+            self.path = path
+        with np.load(self.path, allow_pickle=True) as archive:
+            info = np_io.read_np_archive(archive)
+        K = self.Keys
+        if K.VER.value in info:
+            self.ver = int(info[K.VER.value])
+        if K.COLS.value in info:
+            self.cols = [str(c) for c in info[K.COLS.value]]
+        if K.BLOBS.value in info:
+            self.blobs = info[K.BLOBS.value]
+        for key, attr in ((K.COLOCS, "colocalizations"), (K.RESOLUTIONS, "resolutions"),
+                          (K.BASENAME, "basename"), (K.ROI_OFFSET, "roi_offset"),
+                          (K.ROI_SIZE, "roi_size")):
+            if key.value in info:
+                val = info[key.value]
+                if isinstance(val, np.ndarray) and val.dtype == object and val.ndim == 0:
+                    val = val.item()
+                setattr(self, attr, val)
+        if self.ver <= 4 and self.cols is not None:
+            # v4 archives listed abs-coordinate names for columns that had been dropped
+            self.cols = self.cols[:len(self.cols) - 3]
+        self.ver = self.BLOBS_NP_VER
+        return self
+
+    def save_archive(self, to_add=None, update: bool = False):
+        """Write the archive with the reference's keys, backing up an existing
+        file first (detector.py:269-323)."""
+        if to_add is None:
+            present = {k: v for k, v in self._col_inds.items() if v is not None}
+            K = self.Keys
+            arc = {
+                K.VER.value: self.ver, K.BLOBS.value: self.blobs,
+                K.RESOLUTIONS.value: self.resolutions, K.BASENAME.value: self.basename,
+                K.ROI_OFFSET.value: self.roi_offset, K.ROI_SIZE.value: self.roi_size,
+                K.COLOCS.value: self.colocalizations,
+                K.COLS.value: [k.value for k, _ in sorted(present.items(), key=lambda e: e[1])],
+            }
+        else:
+            arc = to_add
+        if update:
+            with np.load(self.path, allow_pickle=True) as archive:
+                arc = np_io.read_np_archive(archive)
+                arc.update(to_add)
+        libmag.backup_file(self.path)
+        with open(self.path, "wb") as f:
+            np.savez(f, **arc)
+        return arc
+
+    # -- column accessors -----------------------------------------------------------
+    @classmethod
+    def _get_col_as_ind(cls, col):
+        if libmag.is_seq(col):
+            return [cls._col_inds[c] if isinstance(c, cls.Cols) else c for c in col]
+        return cls._col_inds[col] if isinstance(col, cls.Cols) else col
+
+    @classmethod
+    def _get_rel_inds(cls) -> List[int]:
+        return [cls._col_inds[c] for c in (cls.Cols.Z, cls.Cols.Y, cls.Cols.X)]
+
+    @classmethod
+    def _get_abs_inds(cls) -> List[int]:
+        return [cls._col_inds[c] for c in (cls.Cols.ABS_Z, cls.Cols.ABS_Y, cls.Cols.ABS_X)]
+
+    @classmethod
+    def get_blob_col(cls, blob: np.ndarray, col):
+        if col is None:
+            return np.array([]) if blob.ndim > 1 else None
+        col = cls._get_col_as_ind(col)
+        return blob[..., col] if blob.ndim > 1 else blob[col]
+
+    @classmethod
+    def set_blob_col(cls, blob: np.ndarray, col, val, mask=np.s_[:], **kwargs) -> np.ndarray:
+        col = cls._get_col_as_ind(col)
+        if blob.ndim > 1:
+            blob[mask, ..., col] = val
+        else:
+            blob[col] = val
+        return blob
+
+    @classmethod
+    def get_blob_confirmed(cls, blob):
+        return cls.get_blob_col(blob, cls._col_inds[cls.Cols.CONFIRMED])
+
+    @classmethod
+    def set_blob_confirmed(cls, blob, *args, **kwargs):
+        return cls.set_blob_col(blob, cls._col_inds[cls.Cols.CONFIRMED], *args, **kwargs)
+
+    @classmethod
+    def get_blob_truth(cls, blob):
+        return cls.get_blob_col(blob, cls._col_inds[cls.Cols.TRUTH])
+
+    @classmethod
+    def set_blob_truth(cls, blob, *args, **kwargs):
+        return cls.set_blob_col(blob, cls._col_inds[cls.Cols.TRUTH], *args, **kwargs)
+
+    @classmethod
+    def get_blobs_channel(cls, blob):
+        return cls.get_blob_col(blob, cls._col_inds[cls.Cols.CHANNEL])
+
+    @classmethod
+    def set_blob_channel(cls, blob, *args, **kwargs):
+        return cls.set_blob_col(blob, cls._col_inds[cls.Cols.CHANNEL], *args, **kwargs)
+
+    @classmethod
+    def get_blob_abs_coords(cls, blobs):
+        return cls.get_blob_col(blobs, cls._get_abs_inds())
+
+    @classmethod
+    def set_blob_abs_coords(cls, blobs, coords, *args, **kwargs):
+        cls.set_blob_col(blobs, cls._get_abs_inds(), coords, *args, **kwargs)
+        return blobs
+
+    # -- coordinate shifts ------------------------------------------------------------
+    @classmethod
+    def shift_blobs(cls, blob, cols, fn: Callable, vals, to_int: bool = False):
+        if blob is None:
+            return blob
+        sub = fn(blob[cols] if blob.ndim == 1 else blob[..., cols], vals)
+        if to_int:
+            sub = sub.astype(int)
+        if blob.ndim == 1:
+            blob[cols] = sub
+        else:
+            blob[..., cols] = sub
+        return blob
+
+    @classmethod
+    def shift_blob_rel_coords(cls, blob, offset):
+        return cls.shift_blobs(blob, cls._get_rel_inds(), np.add, offset)
+
+    @classmethod
+    def shift_blob_abs_coords(cls, blob, offset):
+        return cls.shift_blobs(blob, cls._get_abs_inds(), np.add, offset)
+
+    @classmethod
+    def multiply_blob_rel_coords(cls, blob, factor):
+        return cls.shift_blobs(blob, cls._get_rel_inds(), np.multiply, factor, True)
+
+    @classmethod
+    def multiply_blob_abs_coords(cls, blob, factor):
+        return cls.shift_blobs(blob, cls._get_abs_inds(), np.multiply, factor, True)
+
+    def remove_abs_blob_coords(self, remove_extra: bool = False) -> np.ndarray:
+        """Drop the abs-coordinate columns; ``remove_extra`` also drops columns
+        not named in ``Cols`` (detector.py:711-731)."""
+        inds = Blobs._col_inds.values() if remove_extra else range(self.blobs.shape[1])
+        abs_inds = Blobs._get_abs_inds()
+        keep = [i for i in inds if i is not None and i not in abs_inds]
+        new_cols = [self.cols[i] for i in keep]
+        self.blobs = self.blobs[:, keep]
+        self.cols = new_cols
+        return self.blobs
+
+    @classmethod
+    def replace_rel_with_abs_blob_coords(cls, blobs: np.ndarray) -> np.ndarray:
+        blobs[:, cls._get_rel_inds()] = blobs[:, cls._get_abs_inds()]
+        return blobs
+
+    @classmethod
+    def blobs_in_channel(cls, blobs, channel, return_mask: bool = False):
+        mask = None
+        sel = blobs
+        if channel is not None:
+            mask = np.isin(cls.get_blobs_channel(blobs), channel)
+            sel = blobs[mask]
+        return (sel, mask) if return_mask else sel
+
+    @classmethod
+    def show_blobs_per_channel(cls, blobs):
+        for chl in np.unique(cls.get_blobs_channel(blobs)):
+            _logger.info("- blobs in channel %s: %s", int(chl),
+                         len(cls.blobs_in_channel(blobs, chl)))
+
+    @classmethod
+    def blob_for_db(cls, blob: np.ndarray) -> np.ndarray:
+        """``abs_z, abs_y, abs_x, radius, confirmed, truth, channel``."""
+        rest = [cls._col_inds[c] for c in (cls.Cols.RADIUS, cls.Cols.CONFIRMED,
+                                           cls.Cols.TRUTH, cls.Cols.CHANNEL)]
+        return np.array([*blob[cls._get_abs_inds()], *blob[rest]])
+
+
+def calc_scaling_factor() -> np.ndarray:
+    """Pixels per physical unit, ``1 / config.resolutions[0]``.
+
+    Raises:
+        AttributeError: if no resolution is set (detector.py:821-823).
+    """
+    if config.resolutions is None or len(config.resolutions) < 1:
+        raise AttributeError("Must load resolutions from file or set a resolution")
+    return np.divide(1.0, config.resolutions[0])
+
+
+def calc_overlap(factor: Optional[int] = None) -> np.ndarray:
+    """Chunk overlap in pixels, ``ceil(scaling * factor)`` (detector.py:828-841)."""
+    if factor is None:
+        factor = OVERLAP_FACTOR
+    return np.ceil(np.multiply(calc_scaling_factor(), factor)).astype(int)
+
+
+def sigma_ladder(settings, scaling_factor: float, image_is_f32: bool = False) -> np.ndarray:
+    """The ``blob_log`` scale ladder for a profile: ``linspace(min_sigma_factor,
+    max_sigma_factor, num_sigma) * x-scaling`` (detector.py:903-927).  skimage
+    builds it in the image's float dtype, so a float32 image gets
+    float32-rounded sigmas."""
+    dt = np.float32 if image_is_f32 else np.float64
+    lo = np.asarray(settings["min_sigma_factor"] * scaling_factor, dtype=dt)
+    hi = np.asarray(settings["max_sigma_factor"] * scaling_factor, dtype=dt)
+    return np.linspace(lo, hi, int(settings["num_sigma"])).astype(np.float64)
+
+
+def input_scale(dtype) -> float:
+    """``skimage.util.img_as_float`` factor for an input dtype."""
+    dtype = np.dtype(dtype)
+    if dtype.kind == "u":
+        return 1.0 / float(np.iinfo(dtype).max)
+    return 1.0
+
+
+def cands_to_blobs(cands: np.ndarray, sigmas: np.ndarray, shape_yx: Sequence[int],
+                   chl: int) -> np.ndarray:
+    """Device candidates -> the reference's formatted table, in
+    ``peak_local_max`` order (descending response, ties in C order)."""
+    Y, X = shape_yx
+    lin = ((cands["z"].astype(np.int64) * Y + cands["y"]) * X + cands["x"]) * len(sigmas) \
+        + cands["s"]
+    order = np.lexsort((lin, -cands["resp"].astype(np.float64)))
+    c = cands[order]
+    table = np.column_stack([c["z"], c["y"], c["x"], sigmas[c["s"]] * math.sqrt(3)]
+                            ).astype(np.float64)
+    return Blobs(table).format_blobs(chl)
+
+
+def detect_blobs(roi, channel: Optional[Sequence[int]],
+                 exclude_border: Optional[Sequence[Sequence[int]]] = None
+                 ) -> Optional[np.ndarray]:
+    """Detect blobs in an ROI with the multi-scale LoG detector.
+
+    Args:
+        roi: ``(z, y, x)`` or ``(z, y, x, c)`` array (numpy, or a CUDA tensor).
+        channel: channels to detect in; None = all.
+        exclude_border: optional ``[start, end]`` pairs of ``z, y, x`` margins
+            whose blobs are dropped.
+
+    Returns:
+        ``(n, 11)`` float64 table in ``Blobs.Cols`` order, or None if nothing
+        was found (detector.py:874-957).
+    """
+    from .. import gpu
+    shape = tuple(roi.shape)
+    multichannel, channels = plot_3d.setup_channels(roi, channel, 3)
+    if config.get_roi_profile(channels[0])["isotropic"] is not None:
+        raise NotImplementedError(
+            "the 'isotropic' resize (cv_nd.make_isotropic) is not accelerated yet")
+    scale = calc_scaling_factor()[2]
+    detector = gpu.ChunkDetector(shape[:3])
+    blobs_all = []
+    for chl in channels:
+        settings = config.get_roi_profile(chl)
+        if getattr(settings, "spectral_unmixing", None):
+            raise NotImplementedError("spectral unmixing is not accelerated yet")
+        src = gpu.as_source(roi, chl if multichannel else None)
+        sigmas = sigma_ladder(settings, scale, src.dtype == gpu._lib.MMB_F32)
+        np_dtype = roi.dtype if isinstance(roi, np.ndarray) else None
+        in_scale = input_scale(np_dtype) if np_dtype is not None else (
+            1.0 / 65535.0 if src.dtype == gpu._lib.MMB_U16 else
+            (1.0 / 255.0 if src.dtype == gpu._lib.MMB_U8 else 1.0))
+        cands, _ = detector.detect(src, sigmas, settings["detection_threshold"],
+                                   settings["overlap"], scale=in_scale)
+        if len(cands) < 1:
+            _logger.debug("No blobs detected for channel %s", chl)
+            continue
+        blobs_all.append(cands_to_blobs(cands, sigmas, shape[1:3], chl))
+    if not blobs_all:
+        return None
+    blobs_all = np.vstack(blobs_all)
+    if exclude_border is not None:
+        blobs_all = get_blobs_interior(blobs_all, shape, *exclude_border)
+    return blobs_all
+
+
+def sort_blobs(blobs: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """Sort by z, then y, then x; returns ``(sorted copy, order)``."""
+    order = np.lexsort((blobs[:, 2], blobs[:, 1], blobs[:, 0]))
+    return blobs[order], order
+
+
+def _find_close_blobs(blobs: np.ndarray, blobs_master: np.ndarray, tol):
+    """Indices ``(close_master, close)`` of every (master, check) pair within
+    ``tol`` on all three axes, in master-major order - computed on the GPU."""
+    import torch
+    from .. import gpu
+    dev = gpu.require_cuda()
+    m = torch.from_numpy(np.ascontiguousarray(blobs_master[:, :3]).astype(np.int32)).to(dev)
+    c = torch.from_numpy(np.ascontiguousarray(blobs[:, :3]).astype(np.int32)).to(dev)
+    last, hit = gpu.prune_seams(m, c, [int(t) for t in np.broadcast_to(tol, (3,))])
+    return last.cpu().numpy(), hit.cpu().numpy().astype(bool)
+
+
+def remove_close_blobs(blobs: np.ndarray, blobs_master: np.ndarray, tol,
+                       chunk_size: int = 1000) -> Tuple[np.ndarray, np.ndarray]:
+    """Drop every blob of ``blobs`` that lies within ``tol`` (per-axis, inclusive)
+    of a blob in ``blobs_master``, and move each matched master's absolute
+    coordinates to the rounded mean with its match (detector.py:1009-1085).
+
+    The box test is done on integer-truncated coordinates, as in the reference
+    (which casts to the smallest signed integer dtype).  When several blobs
+    match one master the reference's repeated fancy-index assignment leaves the
+    LAST match in place, i.e. the matching check blob with the largest index;
+    that rule is applied directly.  ``chunk_size`` is accepted for signature
+    compatibility; the GPU match needs no tiling on the host.
+    """
+    if len(blobs) < 1 or len(blobs_master) < 1:
+        return blobs, blobs_master
+    last, hit = _find_close_blobs(blobs, blobs_master, tol)
+    pruned = blobs[~hit]
+    sel = last >= 0
+    if np.any(sel):
+        abs_inds = Blobs(blobs)._get_abs_inds()
+        between = np.around((blobs_master[np.ix_(sel, abs_inds)]
+                             + blobs[np.ix_(last[sel], abs_inds)]) / 2)
+        blobs_master[np.ix_(sel, abs_inds)] = between
+    return pruned, blobs_master
+
+
+def meas_pruning_ratio(num_blobs_orig, num_blobs_after_pruning, num_blobs_next):
+    """``(original count, pruned/original, pruned/adjacent)`` or None
+    (detector.py:1122-1144)."""
+    if num_blobs_next > 0 and num_blobs_orig > 0:
+        return (num_blobs_orig, num_blobs_after_pruning / num_blobs_orig,
+                num_blobs_after_pruning / num_blobs_next)
+    return None
+
+
+def get_blobs_in_roi(blobs: np.ndarray, offset: Sequence[int], size: Sequence[int],
+                     margin: Sequence[int] = (0, 0, 0), reverse: bool = True
+                     ) -> Tuple[np.ndarray, np.ndarray]:
+    """Blobs inside ``[offset - margin, offset + size + margin)``; ``reverse``
+    means the three triples are given as x,y,z (detector.py:1210-1245)."""
+    if reverse:
+        offset, size, margin = offset[::-1], size[::-1], margin[::-1]
+    mask = np.ones(len(blobs), dtype=bool)
+    for a in range(3):
+        mask &= blobs[:, a] >= offset[a] - margin[a]
+        mask &= blobs[:, a] < offset[a] + size[a] + margin[a]
+    return blobs[mask], mask
+
+
+def get_blobs_interior(blobs: np.ndarray, shape: Sequence[int], pad_start: Sequence[int],
+                       pad_end: Sequence[int]) -> np.ndarray:
+    """Blobs at least ``pad_start`` from the low faces and ``pad_end`` from the
+    high faces of a region of ``shape`` (detector.py:1248-1268)."""
+    mask = np.ones(len(blobs), dtype=bool)
+    for a in range(3):
+        mask &= blobs[:, a] >= pad_start[a]
+        mask &= blobs[:, a] < shape[a] - pad_end[a]
+    return blobs[mask]

@@ -1,0 +1,399 @@
+"""Whole-stack blob detection on the GPU behind ``magmap.cv.stack_detect``.
+
+Mirror of ``magmap/cv/stack_detect.py``: block setup (``:260-335``), the
+per-sub-ROI worker (``:82-172``), the fan-out over sub-ROIs (``:175-257``, a
+``multiprocessing.Pool`` in the reference, a loop of fused GPU chunk launches
+here), seam pruning (``:618-861``) and the two drivers ``detect_blobs_blocks``
+(``:338-517``) and ``detect_blobs_stack`` (``:520-615``).
+
+Chunk-faithful by construction: the same chunk grid, 'reflect' filtering at
+every chunk face, preprocessing blocks anchored at each chunk's origin and the
+same seam pruning, so results are comparable blob for blob with the reference.
+"""
+from __future__ import annotations
+
+import os
+from enum import Enum
+from time import time
+from typing import NamedTuple, Optional, Sequence, Tuple
+
+import numpy as np
+import pandas as pd
+
+from . import chunking, detector
+from ..io import libmag, np_io
+from ..plot import plot_3d
+from ..settings import config, roi_prof
+
+_logger = config.logger.getChild(__name__)
+
+
+class StackTimes(Enum):
+    """Keys of ``stack_detection_times.csv``."""
+    DETECTION = "Detection"
+    PRUNING = "Pruning"
+    TOTAL = "Total_stack"
+
+
+class Blocks(NamedTuple):
+    """Block-processing geometry (stack_detect.py:260-279)."""
+    sub_roi_slices: np.ndarray
+    sub_rois_offsets: np.ndarray
+    denoise_max_shape: Optional[np.ndarray]
+    exclude_border: Optional[Sequence[int]]
+    tol: np.ndarray
+    overlap_base: np.ndarray
+    overlap: np.ndarray
+    overlap_padding: np.ndarray
+    max_pixels: np.ndarray
+
+
+def setup_blocks(settings, shape: Sequence[int]) -> Blocks:
+    """Derive chunk and preprocessing-block geometry from a profile and the
+    image resolution (stack_detect.py:282-335)."""
+    scaling = detector.calc_scaling_factor()
+    denoise_max_shape = None
+    if settings["denoise_size"]:
+        denoise_max_shape = np.ceil(scaling * settings["denoise_size"]).astype(int)
+    overlap_base = detector.calc_overlap()
+    tol = np.multiply(overlap_base, settings["prune_tol_factor"]).astype(int)
+    overlap = overlap_base.copy()
+    overlap_padding = tol.copy()
+    exclude_border = settings["exclude_border"]
+    if exclude_border is not None:
+        # the overlap must exceed twice the excluded border so that no plane is
+        # excluded from both neighbouring chunks; no padding past an excluded border
+        twice = np.multiply(2, exclude_border)
+        overlap = np.where(overlap < twice, twice, overlap)
+        excluded = np.greater(exclude_border, 0)
+        overlap[excluded] += 1
+        overlap_padding[excluded] = 0
+    max_pixels = np.ceil(scaling * settings["segment_size"]).astype(int)
+    slices, offsets = chunking.stack_splitter(shape, max_pixels, overlap)
+    return Blocks(slices, offsets, denoise_max_shape, exclude_border, tol, overlap_base,
+                  overlap, overlap_padding, max_pixels)
+
+
+class StackDetector(object):
+    """Detects blobs sub-ROI by sub-ROI.  Class attributes carry the shared
+    state like the reference's fork-friendly design; here they also cache the
+    GPU workspace between sub-ROIs."""
+    img5d: Optional[np_io.Image5d] = None
+    img = None
+    last_coord = None
+    denoise_max_shape = None
+    exclude_border = None
+    coloc = False
+    channel = None
+    _gpu_detector = None
+
+    @classmethod
+    def _workspace(cls, shape):
+        from .. import gpu
+        det = cls._gpu_detector
+        if det is None or any(s > m for s, m in zip(shape, det.max_shape)):
+            grow = shape if det is None else tuple(max(s, m) for s, m in zip(shape, det.max_shape))
+            cls._gpu_detector = det = gpu.ChunkDetector(grow)
+        return det
+
+    @classmethod
+    def release_workspace(cls):
+        cls._gpu_detector = None
+
+    @classmethod
+    def detect_sub_roi_from_data(cls, coord, sub_roi_slices, offset):
+        return cls.detect_sub_roi(coord, offset, cls.last_coord, cls.denoise_max_shape,
+                                  cls.exclude_border, cls.img5d, cls.img[sub_roi_slices],
+                                  cls.channel, coloc=cls.coloc)
+
+    @classmethod
+    def detect_sub_roi(cls, coord: Sequence[int], offset: Sequence[int],
+                       last_coord: Sequence[int], denoise_max_shape: Optional[Sequence[int]],
+                       exclude_border, img5d, sub_roi, channel: Optional[Sequence[int]],
+                       img_path: Optional[str] = None, coloc: bool = False
+                       ) -> Tuple[Sequence[int], Optional[np.ndarray]]:
+        """Preprocess (per ``denoise_max_shape`` block) and detect one sub-ROI in
+        ONE fused GPU call per channel, then shift the blobs to the sub-ROI's
+        offset (stack_detect.py:82-172)."""
+        from .. import gpu
+        if coloc:
+            raise NotImplementedError("intensity co-localisation is outside the accelerated path")
+        shape = tuple(sub_roi.shape)
+        multichannel, channels = plot_3d.setup_channels(sub_roi, channel, 3)
+        scale = detector.calc_scaling_factor()[2]
+        det = cls._workspace(shape[:3])
+        tables = []
+        for chl in channels:
+            settings = config.get_roi_profile(chl)
+            if settings["isotropic"] is not None:
+                raise NotImplementedError("the 'isotropic' resize is not accelerated yet")
+            src = gpu.as_source(sub_roi, chl if multichannel else None)
+            pre = None
+            in_scale = 1.0
+            f32 = src.dtype == gpu._lib.MMB_F32
+            if denoise_max_shape is not None:
+                pre = plot_3d.preproc_params(settings, chl)
+                f32 = False      # preprocessing yields float64 in the reference
+            else:
+                in_scale = {gpu._lib.MMB_U8: 1 / 255.0, gpu._lib.MMB_U16: 1 / 65535.0}.get(
+                    src.dtype, 1.0)
+            sigmas = detector.sigma_ladder(settings, scale, f32)
+            cands, _ = det.detect(
+                src, sigmas, settings["detection_threshold"], settings["overlap"],
+                scale=in_scale, pre=pre,
+                block_shape=denoise_max_shape if denoise_max_shape is not None else (1, 1, 1))
+            if len(cands):
+                tables.append(detector.cands_to_blobs(cands, sigmas, shape[1:3], chl))
+        segments = np.vstack(tables) if tables else None
+        if segments is not None and exclude_border is not None:
+            exclude = np.array([exclude_border, exclude_border])
+            exclude[0, np.equal(coord, 0)] = 0
+            exclude[1, np.equal(coord, last_coord)] = 0
+            segments = detector.get_blobs_interior(segments, shape, *exclude)
+        if segments is not None:
+            detector.Blobs.shift_blob_rel_coords(segments, offset)
+            detector.Blobs.shift_blob_abs_coords(segments, offset)
+        return coord, segments
+
+    @classmethod
+    def detect_blobs_sub_rois(cls, img5d, img, sub_roi_slices, sub_rois_offsets,
+                              denoise_max_shape, exclude_border, coloc, channel):
+        """Run every sub-ROI through the GPU in z, y, x order and collect the
+        blob tables in an object array shaped like the chunk grid
+        (stack_detect.py:175-257)."""
+        last_coord = np.subtract(sub_roi_slices.shape, 1)
+        cls.img5d, cls.img, cls.last_coord = img5d, img, last_coord
+        cls.denoise_max_shape, cls.exclude_border = denoise_max_shape, exclude_border
+        cls.coloc, cls.channel = coloc, channel
+        seg_rois = np.zeros(sub_roi_slices.shape, dtype=object)
+        # size the workspace once for the largest chunk
+        largest = [max(s[a].stop - s[a].start for s in sub_roi_slices.flat) for a in range(3)]
+        cls._workspace(tuple(largest))
+        for coord in np.ndindex(*sub_roi_slices.shape):
+            _, segments = cls.detect_sub_roi_from_data(
+                coord, sub_roi_slices[coord], sub_rois_offsets[coord])
+            seg_rois[coord] = segments
+        # a table with zero rows is stored as None, like the reference
+        for coord in np.ndindex(*seg_rois.shape):
+            if seg_rois[coord] is not None and len(seg_rois[coord]) == 0:
+                seg_rois[coord] = None
+        return seg_rois
+
+
+class StackPruner(object):
+    """Removes duplicate blobs detected twice in the overlap between
+    neighbouring sub-ROIs (stack_detect.py:618-861)."""
+    blobs_to_prune = None
+
+    @classmethod
+    def prune_overlap_by_index(cls, i):
+        return cls.prune_overlap(i, cls.blobs_to_prune[i])
+
+    @classmethod
+    def prune_overlap(cls, i, pruner):
+        """Within one overlap slab, blobs tagged with chunk ``i`` along ``axis``
+        are the masters and blobs tagged ``i + 1`` are checked against them;
+        blobs of any other chunk in the slab are dropped (stack_detect.py:644-677)."""
+        blobs, axis, tol, blobs_next = pruner
+        if blobs is None:
+            return None, None
+        tag_col = blobs.shape[1] - 3 + axis
+        n_orig = len(blobs)
+        master = blobs[blobs[:, tag_col] == i]
+        check = blobs[blobs[:, tag_col] == i + 1]
+        pruned, master = detector.remove_close_blobs(check, master, tol)
+        merged = np.concatenate((master, pruned))
+        ratios = None
+        if blobs_next is not None:
+            ratios = detector.meas_pruning_ratio(n_orig, len(merged), len(blobs_next))
+        return merged, ratios
+
+    @classmethod
+    def prune_blobs_mp(cls, img, seg_rois, overlap, tol, sub_roi_slices, sub_rois_offsets,
+                       channels, overlap_padding=None):
+        """Prune axis by axis.  For each seam the slab ``[end - (overlap + pad),
+        end + pad)`` of chunk ``j`` is pruned (chunk ``j`` = master, ``j + 1`` =
+        check); blobs outside every slab pass through; the next axis works on
+        the recombined table.  Returns ``(table without chunk tags, DataFrame of
+        pruning ratios)`` or ``(None, None)``."""
+        merged = chunking.merge_blobs(seg_rois)
+        if merged is None:
+            return None, None
+        if overlap_padding is None:
+            overlap_padding = tol
+        cols = ("blobs", "ratio_pruning", "ratio_adjacent")
+        ratios_out = {}
+        per_channel = []
+        last = tuple(np.subtract(sub_roi_slices.shape, 1))
+        for chl in channels:
+            blobs = detector.Blobs.blobs_in_channel(merged, chl)
+            for axis in range(3):
+                n_sec = sub_rois_offsets.shape[axis]
+                if n_sec <= 1:
+                    continue
+                keep_parts = []
+                work = []
+                pos = blobs[:, axis]
+                for j in range(n_sec):
+                    coord = [0, 0, 0]
+                    coord[axis] = j
+                    coord = tuple(coord)
+                    start = sub_rois_offsets[coord][axis]
+                    sl = sub_roi_slices[coord]
+                    size = sl[axis].stop - sl[axis].start
+                    end = start + size
+                    shift = overlap[axis] + overlap_padding[axis]
+                    blobs_ol = blobs_next = None
+                    if j < n_sec - 1:
+                        lo, hi = end - shift, end + overlap_padding[axis]
+                        blobs_ol = blobs[(pos >= lo) & (pos < hi)]
+                        # same-sized region just past the slab, for the ratio metric
+                        nlo = end + tol[axis]
+                        nhi = nlo + overlap[axis] + 2 * overlap_padding[axis]
+                        total = sub_rois_offsets[last][axis] + size
+                        if nlo < total and nhi < total:
+                            blobs_next = blobs[(pos >= nlo) & (pos < nhi)]
+                        upper = lo
+                    else:
+                        upper = end
+                    lower = start + (shift if j > 0 else 0)
+                    keep_parts.append(blobs[(pos < upper) & (pos >= lower)])
+                    work.append((blobs_ol, axis, tol, blobs_next))
+                cls.blobs_to_prune = work
+                pruned_parts = []
+                for j in range(len(work)):
+                    res, ratios = cls.prune_overlap_by_index(j)
+                    if res is not None:
+                        pruned_parts.append(res)
+                    if ratios:
+                        for c, v in zip(cols, ratios):
+                            ratios_out.setdefault(c, []).append(v)
+                blobs = np.concatenate(keep_parts + pruned_parts)
+            per_channel.append(blobs)
+        out = np.vstack(per_channel)[:, :-3]
+        return out, pd.DataFrame(ratios_out)
+
+
+def detect_blobs_blocks(filename_base: str, img5d: np_io.Image5d,
+                        offset: Optional[Sequence[int]] = None,
+                        size: Optional[Sequence[int]] = None,
+                        channels: Optional[Sequence[int]] = None, verify: bool = False,
+                        save_dfs: bool = True, full_roi: bool = False, coloc: bool = False):
+    """Detect blobs in a large image by block processing.
+
+    Returns ``(stats_detection, fdbk, blobs)`` like the reference
+    (stack_detect.py:338-517); verification against a truth database is outside
+    the accelerated path, so the first two are always None.
+
+    Raises:
+        ValueError: if ``img5d.img`` is None.
+    """
+    t_start = time()
+    if img5d.img is None:
+        raise ValueError("Image data is None")
+    if verify:
+        raise NotImplementedError("truth-database verification is outside the accelerated path")
+    image5d = img5d.img
+    subimg_base = filename_base
+    if size is None or offset is None:
+        size = image5d.shape[1:4]
+        offset = (0, 0, 0)
+    else:
+        # named x,y,z as naming.make_subimage_name does (magmap/io/naming.py:9-37)
+        roi_site = "{}x{}".format(tuple(int(v) for v in offset)[::-1],
+                                  tuple(int(v) for v in size)[::-1]).replace(" ", "")
+        subimg_base = libmag.insert_before_ext(filename_base, roi_site, "_")
+    filename_blobs = libmag.combine_paths(subimg_base, config.SUFFIX_BLOBS)
+
+    if full_roi:
+        roi = image5d[0]
+    else:
+        z0, y0, x0 = (int(v) for v in offset)
+        roi = image5d[0, z0:z0 + int(size[0]), y0:y0 + int(size[1]), x0:x0 + int(size[2])]
+    n_chl = 1 if roi.ndim < 4 else roi.shape[3]
+    if n_chl < 2:
+        coloc = False
+
+    t_det = time()
+    if channels is None:
+        _, channels = plot_3d.setup_channels(roi, channels, 3)
+    settings = config.get_roi_profile(channels[0])
+    blocks = setup_blocks(settings, roi.shape)
+    seg_rois = StackDetector.detect_blobs_sub_rois(
+        img5d, roi, blocks.sub_roi_slices, blocks.sub_rois_offsets,
+        blocks.denoise_max_shape, blocks.exclude_border, coloc, channels)
+    detection_time = time() - t_det
+
+    t_prune = time()
+    segments_all, df_pruning = StackPruner.prune_blobs_mp(
+        roi, seg_rois, blocks.overlap, blocks.tol, blocks.sub_roi_slices,
+        blocks.sub_rois_offsets, channels, blocks.overlap_padding)
+    pruning_time = time() - t_prune
+
+    if df_pruning is not None and save_dfs and len(df_pruning.columns):
+        df_pruning.to_csv("blob_ratios.csv", index=False)
+        if "blobs" in df_pruning.columns:
+            w = df_pruning["blobs"]
+            means = {f"mean_{c}": [float(np.sum(df_pruning[c] * w) / np.sum(w))]
+                     for c in df_pruning.columns[1:]}
+            pd.DataFrame(means).to_csv("blob_ratios_means.csv", index=False)
+
+    blobs = detector.Blobs(segments_all, path=filename_blobs)
+    if segments_all is not None:
+        # the abs columns carried the seam-averaged positions; they become the
+        # coordinates and the helper columns go away (stack_detect.py:458-467)
+        blobs.replace_rel_with_abs_blob_coords(segments_all)
+        blobs.blobs = segments_all
+        segments_all = blobs.remove_abs_blob_coords(True)
+
+    blobs.blobs = segments_all
+    blobs.colocalizations = None
+    blobs.resolutions = config.resolutions
+    blobs.basename = os.path.basename(config.filename) if config.filename else None
+    blobs.roi_offset = offset
+    blobs.roi_size = size
+
+    times = {StackTimes.DETECTION: [detection_time], StackTimes.PRUNING: [pruning_time],
+             StackTimes.TOTAL: [time() - t_start]}
+    if save_dfs:
+        pd.DataFrame({k.value: v for k, v in times.items()}).to_csv(
+            "stack_detection_times.csv", index=False)
+    _logger.info("Blob detection %.3f s, pruning %.3f s, blobs %s", detection_time,
+                 pruning_time, 0 if segments_all is None else len(segments_all))
+    blobs.times = times
+    return None, None, blobs
+
+
+def detect_blobs_stack(filename_base: str, img5d: Optional[np_io.Image5d],
+                       subimg_offset: Optional[Sequence[int]] = None,
+                       subimg_size: Optional[Sequence[int]] = None, coloc: bool = False):
+    """Detect blobs in a whole stack, grouping channels whose profiles share the
+    same block settings into one pass, and save the ``*_blobs.npz`` archive
+    (stack_detect.py:520-615).
+
+    Raises:
+        IOError: if there is no image.
+    """
+    if img5d is None or img5d.img is None:
+        raise IOError("No image data available for blob detection")
+    channels = plot_3d.setup_channels(img5d.img, config.channel, 4)[1]
+    channels = list(channels)
+    if roi_prof.ROIProfile.is_identical_settings(
+            [config.get_roi_profile(c) for c in channels], roi_prof.ROIProfile.BLOCK_SIZES):
+        groups = [channels]
+    else:
+        groups = [[c] for c in channels]
+
+    outs = []
+    for chl in groups:
+        _, _, blobs = detect_blobs_blocks(
+            filename_base, img5d, subimg_offset, subimg_size, chl, False,
+            not config.grid_search_profile, img5d.is_roi, coloc)
+        outs.append(blobs)
+    blobs_all = None
+    if outs:
+        blobs_all = outs[0]
+        blobs_all.blobs = libmag.combine_arrs([b.blobs for b in outs if b.blobs is not None])
+        blobs_all.colocalizations = None
+        blobs_all.save_archive()
+    return None, None, blobs_all

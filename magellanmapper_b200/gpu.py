@@ -235,3 +235,13 @@ class ChunkDetector:
                 continue
             _lib.check(rc)
             return cands_to_numpy(self.cand, n_out.value), n_peaks.value
+
+
+def whole_roi_preprocess(src: Source, params: MmbPreprocParams) -> np.ndarray:
+    """``saturate_roi`` / ``denoise_roi`` with the whole ROI as one block (the
+    GUI path).  Only ROIs that fit the one-CTA kernel (<= 32 voxels a side) are
+    implemented so far; larger ones raise ``NotImplementedError``."""
+    Z, Y, X = src.shape
+    out = preprocess_blocks(src, (Z, Y, X), params)
+    torch.cuda.synchronize()
+    return out[:, :, :X].cpu().numpy()

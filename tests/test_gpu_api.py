@@ -1,0 +1,166 @@
+"""GPU tests of the reference-facing Python surface (detector.detect_blobs,
+stack_detect.detect_blobs_blocks / detect_blobs_stack, StackPruner) against the
+reference-generated vectors and the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+from oracle import magmap_restated as mm                      # noqa: E402
+from magellanmapper_b200 import synth                         # noqa: E402
+from magellanmapper_b200.cv import detector, stack_detect     # noqa: E402
+from magellanmapper_b200.io import np_io                      # noqa: E402
+from magellanmapper_b200.settings import config, roi_prof     # noqa: E402
+
+
+@pytest.fixture(autouse=True)
+def _cuda():
+    from magellanmapper_b200 import gpu
+    gpu.require_cuda()
+    yield
+    stack_detect.StackDetector.release_workspace()
+
+
+def _setup(resolution=(1, 1, 1), near_max=-1.0, **mods):
+    prof = roi_prof.ROIProfile()
+    prof.add_profiles("roi_blobs.yaml")
+    for k, v in mods.items():
+        prof[k] = v
+    config.roi_profile = prof
+    config.roi_profiles = [prof]
+    config.resolutions = [list(resolution)]
+    config.near_max = [near_max]
+    config.channel = None
+    return prof
+
+
+def _rows(t):
+    """order-independent view of a blob table: integer z,y,x + radius"""
+    return sorted((int(r[0]), int(r[1]), int(r[2]), round(float(r[3]), 9)) for r in t)
+
+
+def test_detect_blobs_vs_reference_vectors(golden_dir):
+    g = np.load(os.path.join(golden_dir, "detect_small.npz"))
+    _setup(near_max=float(g["near_max"]))
+    raw = detector.detect_blobs(g["vol"], [0])
+    assert raw.shape[1] == 11 and raw.dtype == np.float64
+    assert _rows(raw) == _rows(g["raw"])
+    # identical row ORDER too (descending response) and identical non-coordinate columns
+    np.testing.assert_array_equal(raw[:, 4:7], g["raw"][:, 4:7])
+    np.testing.assert_array_equal(raw[:, 7:10], raw[:, 0:3])
+    assert np.mean(np.all(raw[:, :4] == g["raw"][:, :4], axis=1)) > 0.95
+    gui = detector.detect_blobs(g["pre"], [0])
+    assert _rows(gui) == _rows(g["gui"])
+    excl = detector.detect_blobs(g["pre"], [0], np.array([[3, 4, 5], [2, 0, 6]]))
+    assert _rows(excl) == _rows(g["excl"])
+
+
+def test_detect_blobs_none_when_empty():
+    _setup()
+    assert detector.detect_blobs(np.full((10, 30, 30), 7, dtype=np.uint16), [0]) is None
+
+
+def test_detect_blobs_two_channels_one_call():
+    """channel-last input, per-channel profiles (BASELINE config 4 shape of call)"""
+    v0, _ = synth.make_volume((30, 70, 80), seed=51, density=1 / 2500.0)
+    v1, _ = synth.make_volume((30, 70, 80), seed=52, density=1 / 2500.0)
+    roi = np.stack([v0, v1], axis=-1)
+    p0 = _setup()
+    p1 = roi_prof.ROIProfile()
+    p1.add_profiles("roi_blobs.yaml")
+    p1["min_sigma_factor"], p1["max_sigma_factor"] = 4, 10
+    config.roi_profiles = [p0, p1]
+    both = detector.detect_blobs(roi, None)
+    want0 = mm.detect_blobs(v0, mm.Profile(), (1, 1, 1), 0)
+    want1 = mm.detect_blobs(v1, mm.Profile(min_sigma_factor=4, max_sigma_factor=10), (1, 1, 1), 1)
+    assert _rows(both[both[:, 6] == 0]) == _rows(want0)
+    assert _rows(both[both[:, 6] == 1]) == _rows(want1)
+
+
+def test_remove_close_blobs_vs_reference_vectors(golden_dir):
+    g = np.load(os.path.join(golden_dir, "remove_close.npz"))
+    for i in range(int(g["n"])):
+        pruned, master = detector.remove_close_blobs(
+            g[f"r{i}_check"].copy(), g[f"r{i}_master"].copy(), g[f"r{i}_tol"])
+        np.testing.assert_array_equal(pruned, g[f"r{i}_pruned"])
+        np.testing.assert_array_equal(master, g[f"r{i}_master_out"])
+
+
+def test_prune_blobs_mp_vs_reference_vectors(golden_dir):
+    g = np.load(os.path.join(golden_dir, "prune_mp.npz"))
+    prof = _setup(segment_size=50)
+    shape = tuple(g["shape"])
+    b = stack_detect.setup_blocks(prof, shape)
+    seg = np.zeros(tuple(g["grid"]), dtype=object)
+    for c in np.ndindex(*seg.shape):
+        t = g["seg_%d_%d_%d" % c]
+        seg[c] = t.copy() if len(t) else None
+    out, df = stack_detect.StackPruner.prune_blobs_mp(
+        np.zeros(shape, np.uint8), seg, b.overlap, b.tol, b.sub_roi_slices,
+        b.sub_rois_offsets, [0], b.overlap_padding)
+    np.testing.assert_array_equal(out, g["pruned"])
+    assert list(df.columns) == ["blobs", "ratio_pruning", "ratio_adjacent"]
+
+
+@pytest.mark.parametrize("tag,mods", [("plain", {}), ("excl", {"exclude_border": (2, 1, 1)})])
+def test_detect_blobs_blocks_vs_reference_vectors(golden_dir, tmp_path, tag, mods):
+    """The reference's own detect_blobs_blocks output (fork pool, seam pruning)
+    on a 2x3x3-chunk volume must be reproduced row for row."""
+    g = np.load(os.path.join(golden_dir, "stack_small.npz"))
+    _setup(near_max=float(g["near_max"]), segment_size=50, **mods)
+    config.filename = str(tmp_path / "synth")
+    img5d = np_io.Image5d(g["vol"][None])
+    os.chdir(tmp_path)
+    _, _, blobs = stack_detect.detect_blobs_blocks(
+        config.filename, img5d, None, None, [0], False, True, True)
+    want = g[f"{tag}_blobs"]
+    assert blobs.cols == list(g[f"{tag}_cols"])
+    assert blobs.blobs.shape == want.shape
+    np.testing.assert_array_equal(blobs.blobs, want)
+    assert os.path.exists(tmp_path / "stack_detection_times.csv")
+
+
+def test_detect_blobs_stack_saves_archive(golden_dir, tmp_path):
+    g = np.load(os.path.join(golden_dir, "stack_small.npz"))
+    _setup(near_max=float(g["near_max"]), segment_size=50)
+    config.filename = str(tmp_path / "vol")
+    os.chdir(tmp_path)
+    img5d = np_io.Image5d(g["vol"][None])
+    img5d.is_roi = True
+    _, _, blobs = stack_detect.detect_blobs_stack(config.filename, img5d)
+    np.testing.assert_array_equal(blobs.blobs, g["plain_blobs"])
+    back = detector.Blobs().load_blobs(str(tmp_path / "vol_blobs.npz"))
+    np.testing.assert_array_equal(back.blobs, g["plain_blobs"])
+    assert back.cols == ["z", "y", "x", "radius", "confirmed", "truth", "channel", "region"]
+
+
+def test_stack_anisotropic_geometry_vs_oracle(tmp_path):
+    """config 5 geometry (resolution 5x1x1: 5x25x25 preprocessing blocks,
+    100x500x500-voxel chunks scaled down via segment_size) against the oracle."""
+    shape = (40, 120, 110)
+    vol, _ = synth.make_volume(shape, seed=61, density=1 / 2500.0)
+    nm = synth.near_max_of(vol)
+    res = (5, 1, 1)
+    _setup(res, nm, segment_size=60)
+    config.filename = str(tmp_path / "aniso")
+    os.chdir(tmp_path)
+    want = mm.detect_blobs_blocks(vol, mm.Profile(segment_size=60), res, nm)
+    _, _, blobs = stack_detect.detect_blobs_blocks(
+        config.filename, np_io.Image5d(vol[None]), None, None, [0], False, False, True)
+    np.testing.assert_array_equal(blobs.blobs, want)
+    assert len(want) > 20
+
+
+def test_stack_accepts_device_tensor(golden_dir, tmp_path):
+    """A CUDA tensor image is consumed in place (no host round trip)."""
+    g = np.load(os.path.join(golden_dir, "stack_small.npz"))
+    _setup(near_max=float(g["near_max"]), segment_size=50)
+    config.filename = str(tmp_path / "dev")
+    os.chdir(tmp_path)
+    t = torch.from_numpy(g["vol"].view(np.int16)).cuda()[None]
+    _, _, blobs = stack_detect.detect_blobs_blocks(
+        config.filename, np_io.Image5d(t), None, None, [0], False, False, True)
+    np.testing.assert_array_equal(blobs.blobs, g["plain_blobs"])

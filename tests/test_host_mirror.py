@@ -1,0 +1,186 @@
+"""CPU tests of the host-side mirror of the reference interface: the
+reference's own unit tests for this path re-expressed against the drop-in
+(magmap/tests/test_chunking.py, magmap/tests/test_detector.py) and the
+reference-generated geometry vectors."""
+import os
+
+import numpy as np
+import pytest
+
+from magellanmapper_b200.cv import chunking, detector, stack_detect
+from magellanmapper_b200.settings import config, roi_prof
+
+
+def _roi_blobs(**mods):
+    prof = roi_prof.ROIProfile()
+    prof.add_profiles("roi_blobs.yaml")
+    for k, v in mods.items():
+        prof[k] = v
+    config.roi_profile = prof
+    config.roi_profiles = [prof]
+    return prof
+
+
+def _split_remerge(roi, max_pixels, overlap):
+    sl, off = chunking.stack_splitter(roi.shape, max_pixels, overlap)
+    subs = np.empty(sl.shape, dtype=object)
+    for c in np.ndindex(*sl.shape):
+        subs[c] = roi[sl[c]]
+    return chunking.merge_split_stack(subs, max_pixels, overlap)
+
+
+def test_stack_splitter_roundtrip():
+    """magmap/tests/test_chunking.py:47-66"""
+    roi = np.arange(5 * 4 * 4).reshape((5, 4, 4))
+    max_pixels = [1, 3, 3]
+    for ov in ((0, 1, 1), (0, 1, 2), (1, 1, 2)):
+        np.testing.assert_array_equal(roi, _split_remerge(roi, max_pixels, np.array(ov)))
+    config.resolutions = [[6.6, 1.1, 1.1]]
+    np.testing.assert_array_equal(roi, _split_remerge(roi, max_pixels, detector.calc_overlap(2)))
+
+
+def test_merge_split_stack2_roundtrip():
+    roi = np.arange(7 * 9 * 11).reshape((7, 9, 11))
+    # the reference only ever calls these with overlap=None (stack_detect.py:124-149);
+    # like it, the write cursor advances by the first chunk's full shape
+    for mp_, ov in (((3, 4, 5), None), ((2, 9, 4), None), ((7, 9, 11), (2, 2, 2))):
+        sl, _ = chunking.stack_splitter(roi.shape, mp_, ov)
+        subs = np.empty(sl.shape, dtype=object)
+        for c in np.ndindex(*sl.shape):
+            subs[c] = roi[sl[c]]
+        total = chunking.get_split_stack_total_shape(subs, ov)
+        np.testing.assert_array_equal(total, roi.shape)
+        out = np.zeros(tuple(total), dtype=roi.dtype)
+        chunking.merge_split_stack2(subs, ov, 0, out)
+        np.testing.assert_array_equal(out, roi)
+
+
+def test_chunk_geometry_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "chunk_geometry.npz"))
+    for i in range(int(g["n"])):
+        ov = g[f"c{i}_overlap"]
+        ov = None if ov[0] < 0 else ov
+        sl, off = chunking.stack_splitter(g[f"c{i}_shape"], g[f"c{i}_max_pixels"], ov)
+        arr = np.zeros(sl.shape + (3, 2), dtype=np.int64)
+        for c in np.ndindex(*sl.shape):
+            arr[c] = [[s.start, s.stop] for s in sl[c]]
+        np.testing.assert_array_equal(arr, g[f"c{i}_slices"])
+        np.testing.assert_array_equal(off, g[f"c{i}_offsets"])
+        assert off.dtype == g[f"c{i}_offsets"].dtype
+
+
+def test_setup_blocks_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "setup_blocks.npz"))
+    for i in range(int(g["n"])):
+        mods = {}
+        for k in g[f"b{i}_mods_keys"]:
+            v = g[f"b{i}_mod_{k}"]
+            mods[str(k)] = float(v) if v.ndim == 0 else tuple(v.tolist())
+        if "exclude_border" in mods:
+            mods["exclude_border"] = tuple(int(v) for v in mods["exclude_border"])
+        prof = _roi_blobs(**mods)
+        config.resolutions = [g[f"b{i}_res"].tolist()]
+        b = stack_detect.setup_blocks(prof, tuple(g[f"b{i}_shape"]))
+        arr = np.zeros(b.sub_roi_slices.shape + (3, 2), dtype=np.int64)
+        for c in np.ndindex(*b.sub_roi_slices.shape):
+            arr[c] = [[s.start, s.stop] for s in b.sub_roi_slices[c]]
+        np.testing.assert_array_equal(arr, g[f"b{i}_slices"])
+        np.testing.assert_array_equal(b.sub_rois_offsets, g[f"b{i}_offsets"])
+        for key in ("denoise_max_shape", "tol", "overlap_base", "overlap", "overlap_padding",
+                    "max_pixels"):
+            np.testing.assert_array_equal(getattr(b, key), g[f"b{i}_{key}"], err_msg=key)
+
+
+def test_blobs_schema():
+    """magmap/tests/test_detector.py:13-71"""
+    rng = np.random.default_rng(0)
+    blobs = rng.random(20).reshape((5, 4))
+    blobs[:, :3] = np.multiply(blobs[:, :3], 100).astype(int)
+    blobs[:, 3] = blobs[:, 3] * 10
+    bl = detector.Blobs(blobs)
+    assert bl.cols == [c.value for c in bl.Cols][:4]
+    assert bl._col_inds[bl.Cols.RADIUS] == 3
+    assert bl._col_inds[bl.Cols.ABS_X] is None
+    bl.format_blobs()
+    assert bl.cols == [c.value for c in bl.Cols]
+    assert bl._col_inds[bl.Cols.RADIUS] == 3
+    assert bl._col_inds[bl.Cols.ABS_X] == 9
+
+    np.testing.assert_array_equal(bl.get_blob_confirmed(bl.blobs), bl.blobs[:, 4])
+    bl.set_blob_confirmed(bl.blobs, 1)
+    assert np.all(bl.get_blob_confirmed(bl.blobs) == 1)
+    np.testing.assert_array_equal(bl.get_blob_truth(bl.blobs), bl.blobs[:, 5])
+    bl.set_blob_truth(bl.blobs, 2)
+    assert np.all(bl.get_blob_truth(bl.blobs) == 2)
+    np.testing.assert_array_equal(bl.get_blobs_channel(bl.blobs), bl.blobs[:, 6])
+    bl.set_blob_channel(bl.blobs, 3)
+    assert np.all(bl.get_blobs_channel(bl.blobs) == 3)
+    np.testing.assert_array_equal(bl.get_blob_abs_coords(bl.blobs), bl.blobs[:, 7:10])
+    bl.set_blob_abs_coords(bl.blobs, (1, 2, 3))
+    assert all(np.all(bl.get_blob_abs_coords(bl.blobs) == (1, 2, 3), axis=1))
+
+
+def test_blob_layout_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "blob_layout.npz"))
+    bl = detector.Blobs(g["b4"].copy())
+    full = bl.format_blobs(2)
+    np.testing.assert_array_equal(full, g["full"])
+    assert list(g["cols"]) == bl.cols
+    inter = detector.get_blobs_interior(full, (100, 100, 100), (10, 5, 0), (20, 0, 30))
+    np.testing.assert_array_equal(inter, g["interior"])
+
+
+def test_merge_blobs_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "prune_mp.npz"))
+    seg = np.zeros(tuple(g["grid"]), dtype=object)
+    for c in np.ndindex(*seg.shape):
+        t = g["seg_%d_%d_%d" % c]
+        seg[c] = t if len(t) else None
+    np.testing.assert_array_equal(chunking.merge_blobs(seg), g["merged"])
+    empty = np.zeros((2, 1, 1), dtype=object)
+    empty[:] = None
+    assert chunking.merge_blobs(empty) is None
+
+
+def test_archive_roundtrip(tmp_path):
+    rng = np.random.default_rng(1)
+    bl = detector.Blobs(rng.random((6, 4)))
+    bl.format_blobs(0)
+    bl.replace_rel_with_abs_blob_coords(bl.blobs)
+    bl.remove_abs_blob_coords(True)
+    assert bl.cols == ["z", "y", "x", "radius", "confirmed", "truth", "channel", "region"]
+    bl.path = str(tmp_path / "x_blobs.npz")
+    bl.resolutions = [[1.0, 1.0, 1.0]]
+    bl.basename = "x"
+    bl.roi_offset, bl.roi_size = (0, 0, 0), (5, 6, 7)
+    arc = bl.save_archive()
+    assert set(arc) == {"ver", "segments", "resolutions", "basename", "offset", "roi_size",
+                        "colocs", "columns"}
+    bl.save_archive()                      # second save backs the first one up
+    assert os.path.exists(str(tmp_path / "x_blobs(1).npz"))
+    back = detector.Blobs().load_blobs(bl.path)
+    np.testing.assert_array_equal(back.blobs, bl.blobs)
+    assert back.cols == bl.cols and back.ver == 5
+
+
+def test_profile_layers():
+    prof = roi_prof.ROIProfile()
+    assert prof["segment_size"] == 500 and prof["denoise_size"] == 25
+    prof.add_profiles("lightsheet,4xnuc")
+    assert prof["settings_name"] == "default,lightsheet,4xnuc"
+    assert prof["max_sigma_factor"] == 4 and prof["exclude_border"] == (1, 0, 0)
+    a, b = roi_prof.ROIProfile(), roi_prof.ROIProfile()
+    assert roi_prof.ROIProfile.is_identical_settings([a, b], roi_prof.ROIProfile.BLOCK_SIZES)
+    b["segment_size"] = 100
+    assert not roi_prof.ROIProfile.is_identical_settings([a, b], roi_prof.ROIProfile.BLOCK_SIZES)
+
+
+def test_errors_match_reference():
+    config.resolutions = None
+    with pytest.raises(AttributeError):
+        detector.calc_scaling_factor()
+    from magellanmapper_b200.io import np_io
+    with pytest.raises(IOError):
+        stack_detect.detect_blobs_stack("x", None)
+    with pytest.raises(ValueError):
+        stack_detect.detect_blobs_blocks("x", np_io.Image5d(None))
