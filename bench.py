@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""Benchmark of the blob-detection hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One step = one pass of ``detect_blobs_blocks`` (chunked preprocessing, 10-scale
+LoG, 4-D local maxima, overlap pruning, seam pruning) over one synthetic
+cleared-tissue stack.  N=1 runs BASELINE config 2, 512x2048x2048 uint16 with
+the ``roi_blobs`` profile at 1 um isotropic resolution (50 chunks).  N>1 runs
+one such stack per GPU as z-slabs of a N*512-plane volume (see ``--mode``).
+
+Prints ONE JSON line (rank 0).  ``value`` = GVoxel/s with the stack resident in
+HBM; ``e2e`` = the same through the public API from pinned HOST memory,
+host->device copy and result read-back inside the timed region.
+``--impl reference`` times the CPU oracle (the reference algorithm restated on
+scipy, multiprocessing pool over chunks) on a bounded sample instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SHAPE_FULL = (512, 2048, 2048)
+RESOLUTION = (1.0, 1.0, 1.0)
+SEED = 1
+METRIC = "blob_detection_throughput"
+UNIT = "GVoxel/s"
+
+
+# ----------------------------------------------------------------------------
+# synthetic input, generated on the device (same recipe as synth.make_volume)
+# ----------------------------------------------------------------------------
+
+def make_device_volume(shape, seed, device, z_offset=0, z_total=None):
+    """uint16 nuclei volume as an int16-bit tensor (torch has no full uint16).
+    Background N(400, 30), Gaussian nuclei sigma U(2.5, 4.5), amplitude
+    U(0.3, 0.9) * 65535, one per 6.7 k voxels.  Built in float32 plane batches."""
+    import torch
+    Z, Y, X = shape
+    g = torch.Generator(device=device)
+    g.manual_seed(seed * 7919 + z_offset)
+    vol = torch.empty((Z, Y, X), dtype=torch.float32, device=device)
+    for z0 in range(0, Z, 64):
+        z1 = min(Z, z0 + 64)
+        vol[z0:z1].normal_(400.0, 30.0, generator=g)
+    n = max(1, int(round(Z * Y * X / 6700.0)))
+    ctr = torch.rand((n, 3), generator=g, device=device) * torch.tensor(
+        [Z, Y, X], device=device, dtype=torch.float32)
+    sig = torch.rand(n, generator=g, device=device) * 2.0 + 2.5
+    amp = (torch.rand(n, generator=g, device=device) * 0.6 + 0.3) * 65535.0
+    R = 16
+    ax = torch.arange(-R, R + 1, device=device)
+    dz, dy, dx = torch.meshgrid(ax, ax, ax, indexing="ij")
+    offs = torch.stack([dz.reshape(-1), dy.reshape(-1), dx.reshape(-1)], dim=1)  # (K,3)
+    flat = vol.view(-1)
+    B = 192
+    for i in range(0, n, B):
+        c = ctr[i:i + B]
+        base = c.floor().long()
+        pos = base[:, None, :] + offs[None, :, :]                       # (b,K,3)
+        ok = ((pos >= 0) & (pos < torch.tensor([Z, Y, X], device=device))).all(-1)
+        d2 = ((pos.float() - c[:, None, :]) ** 2).sum(-1)
+        val = amp[i:i + B, None] * torch.exp(-0.5 * d2 / (sig[i:i + B, None] ** 2))
+        lin = (pos[..., 0] * Y + pos[..., 1]) * X + pos[..., 2]
+        flat.index_add_(0, lin[ok], val[ok])
+    vol.clamp_(0, 65535).round_()
+    out = vol.to(torch.int32)
+    del vol
+    out = torch.where(out > 32767, out - 65536, out).to(torch.int16)     # uint16 bit pattern
+    return out
+
+
+def near_max_device(vol_i16):
+    """max over z-planes of the per-plane 99.5th percentile (importer metadata)."""
+    import torch
+    best = 0.0
+    for z in range(0, vol_i16.shape[0], max(1, vol_i16.shape[0] // 32)):
+        p = vol_i16[z].to(torch.int32)
+        p = torch.where(p < 0, p + 65536, p).float().flatten()
+        k = int(0.995 * (p.numel() - 1))
+        best = max(best, float(torch.kthvalue(p, k + 1).values))
+    return best
+
+
+# ----------------------------------------------------------------------------
+# clocks sampler
+# ----------------------------------------------------------------------------
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200", "-i", str(self.gpu_index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 8:
+                self.rows.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                  "sw_power_cap"), r[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s in sm if s > 0.5 * (max(mx) if mx else 1)] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------
+# profile / config plumbing
+# ----------------------------------------------------------------------------
+
+def setup_config(near_max, filename):
+    from magellanmapper_b200.settings import config, roi_prof
+    prof = roi_prof.ROIProfile()
+    prof.add_profiles("roi_blobs.yaml")
+    config.roi_profile = prof
+    config.roi_profiles = [prof]
+    config.resolutions = [list(RESOLUTION)]
+    config.near_max = [near_max]
+    config.channel = None
+    config.filename = filename
+    return prof
+
+
+def peaks_json():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+# ----------------------------------------------------------------------------
+# CPU baseline (oracle = the reference algorithm restated on scipy)
+# ----------------------------------------------------------------------------
+
+def cpu_sample_shape(cores):
+    """About 10-30 s of CPU work at ~0.3 MVoxel/s/core, in 64-plane chunks."""
+    target = 0.3e6 * cores * 15.0
+    side = int(max(128, min(1024, (target / 128) ** 0.5)) // 64 * 64)
+    return (128, side, side)
+
+
+def run_cpu_baseline(sample, near_max, cores):
+    from oracle import magmap_restated as mm
+    prof = mm.Profile(segment_size=64)          # 64^3 chunks (+5 overlap): many tasks per core
+    t0 = time.perf_counter()
+    blobs = mm.detect_blobs_blocks(sample, prof, RESOLUTION, near_max, processes=cores)
+    dt = time.perf_counter() - t0
+    return sample.size / dt / 1e9, dt, 0 if blobs is None else len(blobs)
+
+
+# ----------------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--shape", type=str, default=None, help="z,y,x override (testing)")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    shape = tuple(int(v) for v in args.shape.split(",")) if args.shape else SHAPE_FULL
+    cores = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        run_reference(args, rank, world, shape, cores)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from magellanmapper_b200 import gpu, _lib
+    from magellanmapper_b200.cv import stack_detect
+    from magellanmapper_b200.io import np_io
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    lib = _lib.load()
+    gpu.require_cuda()
+
+    tmp = tempfile.mkdtemp(prefix="mmb_bench_")
+    os.chdir(tmp)
+
+    # ---- input: one config-2 stack per rank (weak scaling) -----------------
+    vol = make_device_volume(shape, SEED + rank, device)
+    near_max = near_max_device(vol)
+    if world > 1:
+        t = torch.tensor([near_max], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        near_max = float(t.item())
+    setup_config(near_max, os.path.join(tmp, f"bench_r{rank}"))
+    img5d_dev = np_io.Image5d(vol[None])
+    nvox = float(np.prod(shape))
+
+    def step_resident():
+        _, _, blobs = stack_detect.detect_blobs_blocks(
+            os.path.join(tmp, f"bench_r{rank}"), img5d_dev, None, None, [0], False, False, True)
+        return blobs
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        blobs = step_resident()
+    n_blobs = 0 if blobs.blobs is None else len(blobs.blobs)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.mmb_launch_count()
+    lib.mmb_profile_enable(1)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        step_resident()
+    ev1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = lib.mmb_launch_count() - launches0
+    import ctypes as C
+    ms = (C.c_double * 10)(); cnt = (C.c_int64 * 10)(); units = (C.c_double * 10)()
+    lib.mmb_profile_collect(ms, cnt, units)
+    lib.mmb_profile_enable(0)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # a step ends with host-side table assembly, so the step time is the larger of
+    # the device span and the wall clock between the two synchronisations
+    t_step = max(wall, dev_ms / 1e3)
+    if world > 1:
+        tt = torch.tensor([t_step], device=device, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_step = float(tt.item())
+    value = nvox * world * args.steps / t_step / 1e9
+
+    # ---- e2e: pinned host stack -> public API -> blob table on the host ----
+    e2e = None
+    if not args.skip_e2e:
+        host = torch.empty(vol.shape, dtype=torch.int16).pin_memory()
+        host.copy_(vol)
+        torch.cuda.synchronize()
+        host_np = host.numpy().view(np.uint16)
+        img5d_host = np_io.Image5d(host_np[None])
+        img5d_host.is_roi = True
+
+        def step_e2e():
+            _, _, b = stack_detect.detect_blobs_stack(os.path.join(tmp, f"e2e_r{rank}"),
+                                                      img5d_host)
+            return b
+
+        b = step_e2e()                                    # warm the pinned path once
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            b = step_e2e()
+        barrier()
+        t_e2e = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([t_e2e], device=device, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_e2e = float(tt.item())
+        d2h = 0 if b.blobs is None else int(b.blobs.shape[0]) * 20
+        e2e = {"value": nvox * world * args.steps / t_e2e / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": int(nvox * 2), "d2h_bytes_per_step": d2h}
+        del host, host_np, img5d_host
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (y sweep: 8 B in + 8 B out per voxel) --
+    peaks, peak_src = peaks_json()
+    kinds = ["to_float", "preprocess", "log_x", "log_y", "log_z", "localmax", "prune_edges",
+             "prune_resolve", "compact", "seam_match"]
+    alg_bytes = {"preprocess": 6.0, "log_x": 12.0, "log_y": 16.0, "log_z": 12.0, "localmax": 4.0}
+    per_kind = {}
+    total_ms = sum(ms)
+    for i, k in enumerate(kinds):
+        if cnt[i]:
+            per_kind[k] = {"ms": ms[i], "launches": int(cnt[i]), "share": ms[i] / total_ms,
+                           "gbps": (alg_bytes[k] * units[i] / (ms[i] * 1e-3) / 1e9
+                                    if k in alg_bytes else None)}
+    dom = max((k for k in per_kind if k in alg_bytes), key=lambda k: per_kind[k]["ms"])
+    roof = {"bound": "hbm", "kernel": dom, "achieved": per_kind[dom]["gbps"],
+            "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": per_kind[dom]["gbps"] / peaks["hbm_gbs"], "traffic": None,
+            "peak_source": f"{peak_src} copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
+            "avg_launch_ms": per_kind[dom]["ms"] / per_kind[dom]["launches"],
+            "algorithmic_bytes_per_voxel": alg_bytes[dom],
+            "fp32_colimit": "sweeps issue (14 r + 7) FFMA per voxel per scale, r = 12..20: "
+                            "FP32-issue bound before HBM bound (DESIGN.md)",
+            "per_kernel": per_kind}
+
+    cpu = None
+    if not args.skip_cpu:
+        sshape = cpu_sample_shape(cores)
+        sshape = tuple(min(a, b) for a, b in zip(sshape, shape))
+        sample = vol[:sshape[0], :sshape[1], :sshape[2]].cpu().numpy().view(np.uint16)
+        gv, dt, nb = run_cpu_baseline(np.ascontiguousarray(sample), near_max, cores)
+        cpu = {"value": gv, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{sshape[0]}x{sshape[1]}x{sshape[2]} corner of the same stack, "
+                         f"64^3-voxel chunks, fork pool of {cores} processes, {dt:.1f} s, "
+                         f"{nb} blobs"}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t_step / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"BASELINE config 2: synthetic cleared-tissue stack "
+                               f"{shape[0]}x{shape[1]}x{shape[2]} uint16 per GPU, roi_blobs "
+                               f"profile, detect_blobs_blocks (25^3 block preprocessing, 10-scale "
+                               f"LoG sigma 3..5, 4-D local maxima, overlap + seam pruning), "
+                               f"chunk-faithful, 500^3-voxel chunks with 5-voxel overlap",
+                   "l2": "inputs larger than L2 (every sweep streams >= 1 GB per launch)",
+                   "blobs_per_step": n_blobs},
+        "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+        "clocks": clocks,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args, rank, world, shape, cores):
+    """Reference arm: the reference's CPU algorithm (oracle port; scikit-image is
+    not installable here) with a fork pool over all host cores, on a bounded
+    sample of the same workload."""
+    if rank != 0:
+        return
+    from magellanmapper_b200 import synth
+    sshape = tuple(min(a, b) for a, b in zip(cpu_sample_shape(cores), shape))
+    sample, _ = synth.make_volume(sshape, SEED)
+    near_max = synth.near_max_of(sample)
+    for _ in range(min(args.warmup, 1)):
+        run_cpu_baseline(sample, near_max, cores)
+    t_tot, nb = 0.0, 0
+    for _ in range(args.steps):
+        gv, dt, nb = run_cpu_baseline(sample, near_max, cores)
+        t_tot += dt
+    value = sample.size * args.steps / t_tot / 1e9
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": t_tot / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"bounded sample {sshape[0]}x{sshape[1]}x{sshape[2]} of BASELINE "
+                               f"config 2 (same generator and profile), 64^3-voxel chunks"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sshape[0]}x{sshape[1]}x{sshape[2]}, fork pool of {cores}, "
+                                   f"{nb} blobs"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -151,6 +151,18 @@ int mmb_detect_chunk(const void* in, int dtype, const int64_t in_strides[3],
  * gpu_launches).                                                              */
 int64_t mmb_launch_count(void);
 
+/* Optional per-kernel timing with CUDA events recorded on the launching stream
+ * around every kernel (bench.py's roofline).  mmb_profile_enable(1) clears and
+ * starts recording, (0) stops.  mmb_profile_collect synchronises the recorded
+ * events and sums, per kernel kind, elapsed milliseconds, launch count and work
+ * units (voxels; candidates for the prune kernels; pairs for the seam match).
+ * Kinds: 0 to_float, 1 preprocess, 2 log_x, 3 log_y, 4 log_z, 5 localmax,
+ * 6 prune_edges, 7 prune_resolve, 8 compact, 9 seam_match.                    */
+#define MMB_PROF_NKINDS 10
+int mmb_profile_enable(int on);
+int mmb_profile_collect(double ms[MMB_PROF_NKINDS], int64_t launches[MMB_PROF_NKINDS],
+                        double units[MMB_PROF_NKINDS]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,6 +49,9 @@ SIGNATURES = {
     "mmb_version": (C.c_int, []),
     "mmb_last_error": (C.c_char_p, []),
     "mmb_launch_count": (C.c_int64, []),
+    "mmb_profile_enable": (C.c_int, [C.c_int]),
+    "mmb_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64),
+                                      C.POINTER(C.c_double)]),
     "mmb_to_float": (C.c_int, [_vp, C.c_int, _I64x3, C.c_int, C.c_int, C.c_int, _vp,
                                C.c_int64, C.c_double, _vp]),
     "mmb_preprocess_blocks": (C.c_int, [_vp, C.c_int, _I64x3, C.c_int, C.c_int, C.c_int,

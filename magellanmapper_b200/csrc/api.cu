@@ -1,6 +1,7 @@
 // Library-wide state and the fused per-chunk driver.
 #include <stdarg.h>
 #include <string.h>
+#include <mutex>
 #include <vector>
 #include "common.cuh"
 
@@ -14,6 +15,25 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+// ---- optional event profiling ---------------------------------------------------
+struct ProfRec { int kind; double units; cudaEvent_t a, b; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+static std::atomic<bool> g_prof_on{false};
+static thread_local ProfRec t_open;
+
+bool prof_enabled() { return g_prof_on.load(std::memory_order_relaxed); }
+void prof_begin(int kind, double units, cudaStream_t st) {
+  t_open.kind = kind; t_open.units = units;
+  cudaEventCreate(&t_open.a); cudaEventCreate(&t_open.b);
+  cudaEventRecord(t_open.a, st);
+}
+void prof_end(cudaStream_t st) {
+  cudaEventRecord(t_open.b, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(t_open);
 }
 
 // implemented in the other translation units
@@ -53,6 +73,29 @@ using namespace mmb;
 extern "C" int mmb_version(void) { return MMB_VERSION; }
 extern "C" const char* mmb_last_error(void) { return g_err; }
 extern "C" int64_t mmb_launch_count(void) { return g_launches.load(); }
+
+extern "C" int mmb_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.clear();
+  g_prof_on.store(on != 0);
+  return MMB_OK;
+}
+
+extern "C" int mmb_profile_collect(double* ms, int64_t* launches, double* units) {
+  MMB_REQUIRE(ms && launches && units, "null output");
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int k = 0; k < PROF_NKINDS; ++k) { ms[k] = 0.0; launches[k] = 0; units[k] = 0.0; }
+  for (auto& r : g_prof) {
+    MMB_CHECK_CUDA(cudaEventSynchronize(r.b));
+    float t = 0.f;
+    MMB_CHECK_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    ms[r.kind] += t; launches[r.kind] += 1; units[r.kind] += r.units;
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  return MMB_OK;
+}
 
 // work layout: [F][ring0][ring1][ring2][A][B][C][D][cand2 (capacity)][keep][counter]
 extern "C" int64_t mmb_detect_work_bytes(int Z, int Y, int64_t pitch, int capacity) {
@@ -122,7 +165,10 @@ extern "C" int mmb_detect_chunk(const void* in, int dtype, const int64_t in_stri
   rc = prune_within_impl(cand2, n, sigmas, num_sigma, overlap, Y, X, keep, st);
   if (rc) return rc;
   MMB_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
-  compact_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(cand2, keep, n, cand, counter);
+  {
+    ProfScope ps(PROF_COMPACT, n, st);
+    compact_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(cand2, keep, n, cand, counter);
+  }
   MMB_CHECK_LAUNCH();
   MMB_CHECK_CUDA(cudaMemcpyAsync(n_out, counter, sizeof(int), cudaMemcpyDeviceToHost, st));
   MMB_CHECK_CUDA(cudaStreamSynchronize(st));

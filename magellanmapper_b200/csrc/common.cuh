@@ -64,4 +64,23 @@ int make_log_weights(double sigma, LogWeights* w);
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Optional per-kernel timing with CUDA events on the launching stream
+// (mmb_profile_enable / mmb_profile_collect).  Kinds index mmb_profile_collect's
+// output arrays.
+enum ProfKind {
+  PROF_TO_FLOAT = 0, PROF_PREPROCESS, PROF_LOG_X, PROF_LOG_Y, PROF_LOG_Z, PROF_LOCALMAX,
+  PROF_PRUNE_EDGES, PROF_PRUNE_RESOLVE, PROF_COMPACT, PROF_SEAM, PROF_NKINDS
+};
+bool prof_enabled();
+void prof_begin(int kind, double units, cudaStream_t st);
+void prof_end(cudaStream_t st);
+struct ProfScope {
+  cudaStream_t st;
+  bool on;
+  ProfScope(int kind, double units, cudaStream_t s) : st(s), on(prof_enabled()) {
+    if (on) prof_begin(kind, units, st);
+  }
+  ~ProfScope() { if (on) prof_end(st); }
+};
+
 }  // namespace mmb

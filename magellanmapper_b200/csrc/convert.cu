@@ -22,6 +22,7 @@ int to_float_impl(const void* in, int dtype, const int64_t st[3], int Z, int Y, 
                   float* out, int64_t pitch, double scale, cudaStream_t s) {
   dim3 grid((unsigned)cdiv(X, 256), (unsigned)Y, (unsigned)Z);
   const float fs = (float)scale;
+  ProfScope ps(PROF_TO_FLOAT, (double)Z * Y * X, s);
   switch (dtype) {
     case MMB_U8:
       to_float_kernel<uint8_t><<<grid, 256, 0, s>>>((const uint8_t*)in, st[0], st[1], st[2], Y, X, out, pitch, fs, scale);

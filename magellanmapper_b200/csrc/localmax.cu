@@ -67,6 +67,7 @@ int localmax_impl(const float* prev, const float* cur, const float* next, int Z,
   for (int z0 = 0; z0 < nz; z0 += 65535) {
     const int zn = nz - z0 < 65535 ? nz - z0 : 65535;
     dim3 grid((unsigned)cdiv(X, 256), (unsigned)Y, (unsigned)zn);
+    ProfScope ps(PROF_LOCALMAX, (double)zn * Y * X, st);
     localmax_kernel<<<grid, 256, 0, st>>>(prev, cur, next, Z, Y, X, pitch, s, thr, z_lo + z0,
                                           z_hi, out, capacity, counter);
     MMB_CHECK_LAUNCH();

@@ -11,6 +11,8 @@ static int run(const float* in0, const float* in1, float* out0, float* out1, int
                int64_t inner, int64_t outer, const LogWeights& w, float scale,
                cudaStream_t st) {
   dim3 grid((unsigned)cdiv(inner, kThreads), (unsigned)cdiv(n_axis, kNB), (unsigned)outer);
+  // outer == 1 is the z sweep (whole y-x plane contiguous), otherwise the y sweep
+  ProfScope ps(outer == 1 ? PROF_LOG_Z : PROF_LOG_Y, (double)inner * n_axis * outer, st);
   conv_strided_kernel<R, 1, kNB, kThreads><<<grid, kThreads, 0, st>>>(
       in0, in1, out0, out1, n_axis, inner, (int64_t)n_axis * inner, w, scale);
   MMB_CHECK_LAUNCH();

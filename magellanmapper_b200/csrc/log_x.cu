@@ -10,6 +10,7 @@ template <int R>
 static int run_x(const float* in, float* outA, float* outB, int64_t nrows, int X,
                  int64_t pitch, const LogWeights& w, cudaStream_t st) {
   dim3 grid((unsigned)cdiv(nrows, 32), (unsigned)cdiv(X, kNBx * kNSEG));
+  ProfScope ps(PROF_LOG_X, (double)nrows * pitch, st);
   conv_x_first_kernel<R, kNBx, kNSEG><<<grid, 32 * kNSEG, 0, st>>>(in, outA, outB, nrows, X,
                                                                   pitch, w);
   MMB_CHECK_LAUNCH();

@@ -357,6 +357,7 @@ static int launch_pre(const void* in, const PreGeom& g, const mmb_preproc_params
     configured = true;
   }
   const int64_t nblocks = (int64_t)g.nbz * g.nby * g.nbx;
+  ProfScope ps(PROF_PREPROCESS, (double)g.Z * g.Y * g.X, st);
   kern<<<(unsigned)nblocks, kPreThreads, smem, st>>>((const T*)in, g, p, mats, mat_pitch, out);
   MMB_CHECK_LAUNCH();
   return MMB_OK;

@@ -160,8 +160,11 @@ int prune_within_impl(const mmb_cand* cand, int n, const double* sigmas_host, in
   for (int attempt = 0; attempt < 2; ++attempt) {
     MMB_CHECK_CUDA(cudaMallocAsync((void**)&d_edges, (size_t)edge_cap * sizeof(int2), st));
     MMB_CHECK_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), st));
-    prune_edges_kernel<<<(unsigned)cdiv(n, kTile), kTile, 0, st>>>(
-        cand, n, d_sig, num_sigma, overlap, Y, X, d_edges, edge_cap, d_count);
+    {
+      ProfScope ps(PROF_PRUNE_EDGES, n, st);
+      prune_edges_kernel<<<(unsigned)cdiv(n, kTile), kTile, 0, st>>>(
+          cand, n, d_sig, num_sigma, overlap, Y, X, d_edges, edge_cap, d_count);
+    }
     MMB_CHECK_LAUNCH();
     MMB_CHECK_CUDA(cudaMemcpyAsync(&n_edges, d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
     MMB_CHECK_CUDA(cudaStreamSynchronize(st));
@@ -174,7 +177,10 @@ int prune_within_impl(const mmb_cand* cand, int n, const double* sigmas_host, in
     set_error("kill-edge buffer overflow (%d > %d)", n_edges, edge_cap);
     return MMB_ERR_OVERFLOW;
   }
-  prune_resolve_kernel<<<1, 1024, 0, st>>>(n, d_edges, n_edges, d_state, d_state + npad, keep);
+  {
+    ProfScope ps(PROF_PRUNE_RESOLVE, n, st);
+    prune_resolve_kernel<<<1, 1024, 0, st>>>(n, d_edges, n_edges, d_state, d_state + npad, keep);
+  }
   MMB_CHECK_LAUNCH();
   MMB_CHECK_CUDA(cudaFreeAsync(d_edges, st));
   MMB_CHECK_CUDA(cudaFreeAsync(d_state, st));
@@ -218,8 +224,11 @@ int prune_seams_impl(const int32_t* master, int nm, const int32_t* check, int nc
                      cudaStream_t st) {
   if (nc > 0) MMB_CHECK_CUDA(cudaMemsetAsync(check_hit, 0, nc, st));
   if (nm == 0) return MMB_OK;
-  seam_match_kernel<<<(unsigned)cdiv(nm, kTile), kTile, 0, st>>>(
-      master, nm, check, nc, tol[0], tol[1], tol[2], master_last, check_hit);
+  {
+    ProfScope ps(PROF_SEAM, (double)nm * nc, st);
+    seam_match_kernel<<<(unsigned)cdiv(nm, kTile), kTile, 0, st>>>(
+        master, nm, check, nc, tol[0], tol[1], tol[2], master_last, check_hit);
+  }
   MMB_CHECK_LAUNCH();
   return MMB_OK;
 }

@@ -161,7 +161,11 @@ class StackDetector(object):
         """Run every sub-ROI through the GPU in z, y, x order and collect the
         blob tables in an object array shaped like the chunk grid
         (stack_detect.py:175-257)."""
+        from .. import gpu
         last_coord = np.subtract(sub_roi_slices.shape, 1)
+        # a host image that fits is moved to the device once (one large DMA, fast
+        # from pinned memory); sub-ROIs are then strided views of it
+        img = gpu.upload_if_fits(img)
         cls.img5d, cls.img, cls.last_coord = img5d, img, last_coord
         cls.denoise_max_shape, cls.exclude_border = denoise_max_shape, exclude_border
         cls.coloc, cls.channel = coloc, channel

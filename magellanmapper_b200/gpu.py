@@ -96,6 +96,24 @@ def as_source(arr, channel: Optional[int] = None, device=None) -> Source:
                   tuple(int(s) for s in view.shape))
 
 
+def upload_if_fits(img, fraction: float = 0.4):
+    """Move a C-contiguous host array to the device in one copy when it takes
+    less than ``fraction`` of the free device memory; otherwise (or for
+    non-contiguous views, e.g. slices of a memmap) return it unchanged and let
+    each sub-ROI be uploaded on its own."""
+    if not isinstance(img, np.ndarray) or not img.flags.c_contiguous:
+        return img
+    if img.dtype not in _NP2MMB:
+        return img
+    device = require_cuda()
+    free, _ = torch.cuda.mem_get_info(device)
+    if img.nbytes > fraction * free:
+        return img
+    host = img.view(np.int16) if img.dtype == np.uint16 else img
+    t = torch.from_numpy(host).to(device, non_blocking=True)
+    return t.view(torch.uint16) if img.dtype == np.uint16 else t
+
+
 def to_float(src: Source, scale: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     lib = _lib.load()
     Z, Y, X = src.shape
