@@ -255,8 +255,7 @@ def main():
             torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        blobs = step_resident()
-    n_blobs = 0 if blobs.blobs is None else len(blobs.blobs)
+        step_resident()
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -268,12 +267,13 @@ def main():
     t0 = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
-        step_resident()
+        blobs = step_resident()
     ev1.record()
     barrier()
     wall = time.perf_counter() - t0
     dev_ms = ev0.elapsed_time(ev1)
     launches = lib.mmb_launch_count() - launches0
+    n_blobs = 0 if blobs.blobs is None else len(blobs.blobs)
     import ctypes as C
     ms = (C.c_double * 10)(); cnt = (C.c_int64 * 10)(); units = (C.c_double * 10)()
     lib.mmb_profile_collect(ms, cnt, units)
