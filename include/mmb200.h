@@ -147,6 +147,24 @@ int mmb_detect_chunk(const void* in, int dtype, const int64_t in_strides[3],
                      mmb_cand* cand, int capacity, int* n_out, int* n_peaks,
                      void* stream);
 
+/* Asynchronous form: enqueues every kernel of the chunk on `stream` and returns
+ * without synchronising; nothing is read back to the host.  `status` is a DEVICE
+ * int32[3] written at the end of the chunk: [0] local maxima found (may exceed
+ * `capacity`), [1] survivors compacted to the front of `cand`, [2] kill edges
+ * found by the overlap pruning (may exceed mmb_detect_edge_capacity(capacity)).
+ * The caller copies `status` and `cand[0 .. status[1])` back after the stream
+ * reaches this point; if [0] > capacity or [2] > edge capacity the results are
+ * incomplete and the chunk must be redone with a larger capacity.  `work` and
+ * `cand` may be reused by the next enqueue on the same stream.  num_sigma <= 64. */
+int mmb_detect_chunk_enqueue(const void* in, int dtype, const int64_t in_strides[3],
+                             int Z, int Y, int X, int64_t pitch, double scale,
+                             const mmb_preproc_params* pre, int bz, int by, int bx,
+                             const double* sigmas, int num_sigma, double threshold,
+                             double overlap, int z_lo, int z_hi, void* work,
+                             mmb_cand* cand, int capacity, int32_t* status,
+                             void* stream);
+int mmb_detect_edge_capacity(int capacity);
+
 /* number of kernels this library has launched in this process (bench.py's
  * gpu_launches).                                                              */
 int64_t mmb_launch_count(void);

@@ -69,6 +69,12 @@ SIGNATURES = {
                                    C.c_int, C.c_int, _vp, _vp]),
     "mmb_prune_seams": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _I32x3, _vp, _vp, _vp]),
     "mmb_detect_work_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int64, C.c_int]),
+    "mmb_detect_edge_capacity": (C.c_int, [C.c_int]),
+    "mmb_detect_chunk_enqueue": (C.c_int, [_vp, C.c_int, _I64x3, C.c_int, C.c_int, C.c_int,
+                                           C.c_int64, C.c_double, C.POINTER(MmbPreprocParams),
+                                           C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double),
+                                           C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
+                                           _vp, _vp, C.c_int, _vp, _vp]),
     "mmb_detect_chunk": (C.c_int, [_vp, C.c_int, _I64x3, C.c_int, C.c_int, C.c_int, C.c_int64,
                                    C.c_double, C.POINTER(MmbPreprocParams), C.c_int, C.c_int,
                                    C.c_int, C.POINTER(C.c_double), C.c_int, C.c_double,

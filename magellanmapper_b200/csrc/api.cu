@@ -3,12 +3,60 @@
 #include <string.h>
 #include <mutex>
 #include <vector>
+#include <cudaTypedefs.h>
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace mmb {
 
+int encode_tensor_map_f32(CUtensorMap* map, const float* base, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
+  static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) ==
+            cudaSuccess && q == cudaDriverEntryPointSuccess)
+      encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  });
+  if (!encode) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return MMB_ERR_CUDA;
+  }
+  cuuint64_t d[5], s[4];
+  cuuint32_t b[5], e[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)base,
+                            d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu x %llu)", (int)r,
+              rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 1));
+    return MMB_ERR_CUDA;
+  }
+  return MMB_OK;
+}
+
 static thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -49,10 +97,18 @@ int localmax_impl(const float* prev, const float* cur, const float* next, int Z,
                   int capacity, int* counter, cudaStream_t st);
 int prune_within_impl(const mmb_cand* cand, int n, const double* sigmas_host, int num_sigma,
                       double overlap, int Y, int X, uint8_t* keep, cudaStream_t st);
+int make_ladder(const double* sigmas_host, int num_sigma, SigmaLadder* out);
+int prune_within_enqueue(const mmb_cand* cand, const int* n_ptr, int n_max,
+                         const SigmaLadder& ladder, double overlap, int Y, int X, int2* edges,
+                         int edge_cap, int* edge_count, unsigned char* state, uint8_t* keep,
+                         cudaStream_t st);
 
 // stable stream compaction of the survivors to the front of a second buffer
 __global__ void compact_kernel(const mmb_cand* __restrict__ in, const uint8_t* __restrict__ keep,
-                               int n, mmb_cand* __restrict__ out, int* __restrict__ counter) {
+                               const int* __restrict__ n_ptr, int n_max,
+                               mmb_cand* __restrict__ out, int* __restrict__ counter) {
+  const int n = min(*n_ptr, n_max);
+  if (blockIdx.x * blockDim.x >= n) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool k = i < n && keep[i];
   const unsigned ballot = __ballot_sync(0xffffffffu, k);
@@ -97,42 +153,65 @@ extern "C" int mmb_profile_collect(double* ms, int64_t* launches, double* units)
   return MMB_OK;
 }
 
-// work layout: [F][ring0][ring1][ring2][A][B][C][D][cand2 (capacity)][keep][counter]
-extern "C" int64_t mmb_detect_work_bytes(int Z, int Y, int64_t pitch, int capacity) {
-  const int64_t vol = align256((int64_t)Z * Y * pitch * (int64_t)sizeof(float));
-  return 8 * vol + align256((int64_t)capacity * (int64_t)sizeof(mmb_cand)) +
-         align256(capacity) + 256;
+// ---- fused per-chunk driver -------------------------------------------------------
+// work layout: [F][ring0][ring1][ring2][A][B][C][D][cand2][keep][edges][state][counters]
+struct ChunkLayout {
+  int64_t vol_b, cand_b, keep_b, edges_b, state_b, total;
+  int edge_cap;
+};
+
+static ChunkLayout chunk_layout(int Z, int Y, int64_t pitch, int capacity) {
+  ChunkLayout L;
+  L.vol_b = align256((int64_t)Z * Y * pitch * (int64_t)sizeof(float));
+  L.cand_b = align256((int64_t)capacity * (int64_t)sizeof(mmb_cand));
+  L.keep_b = align256(capacity);
+  L.edge_cap = 4 * capacity + 4096;
+  L.edges_b = align256((int64_t)L.edge_cap * (int64_t)sizeof(int2));
+  L.state_b = align256(2 * ((int64_t)(capacity + 3) / 4 * 4 + 4));
+  L.total = 8 * L.vol_b + L.cand_b + L.keep_b + L.edges_b + L.state_b + 256;
+  return L;
 }
 
-extern "C" int mmb_detect_chunk(const void* in, int dtype, const int64_t in_strides[3], int Z,
-                                int Y, int X, int64_t pitch, double scale,
-                                const mmb_preproc_params* pre, int bz, int by, int bx,
-                                const double* sigmas, int num_sigma, double threshold,
-                                double overlap, int z_lo, int z_hi, void* work, mmb_cand* cand,
-                                int capacity, int* n_out, int* n_peaks, void* stream) {
-  MMB_REQUIRE(in && in_strides && sigmas && work && cand && n_out, "null buffer");
+extern "C" int64_t mmb_detect_work_bytes(int Z, int Y, int64_t pitch, int capacity) {
+  return chunk_layout(Z, Y, pitch, capacity).total;
+}
+
+// status (device int32[4]): [0] local maxima found (may exceed capacity), [1] survivors
+// written to `cand`, [2] kill edges found (may exceed mmb_detect_edge_capacity(capacity))
+extern "C" int mmb_detect_chunk_enqueue(const void* in, int dtype, const int64_t in_strides[3],
+                                        int Z, int Y, int X, int64_t pitch, double scale,
+                                        const mmb_preproc_params* pre, int bz, int by, int bx,
+                                        const double* sigmas, int num_sigma, double threshold,
+                                        double overlap, int z_lo, int z_hi, void* work,
+                                        mmb_cand* cand, int capacity, int32_t* status,
+                                        void* stream) {
+  MMB_REQUIRE(in && in_strides && sigmas && work && cand && status, "null buffer");
   MMB_REQUIRE(Z > 0 && Y > 0 && X > 0 && pitch >= X, "bad shape");
   MMB_REQUIRE(Y <= 65535 && Z <= 65535, "Y and Z must be <= 65535");
   MMB_REQUIRE(num_sigma > 0 && capacity > 0, "bad sizes");
   MMB_REQUIRE(z_lo >= 0 && z_hi <= Z && z_lo <= z_hi, "bad z range");
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t vol_b = align256((int64_t)Z * Y * pitch * (int64_t)sizeof(float));
+  SigmaLadder ladder;
+  int rc = make_ladder(sigmas, num_sigma, &ladder);
+  if (rc) return rc;
+  const ChunkLayout L = chunk_layout(Z, Y, pitch, capacity);
   char* base = (char*)work;
   float* F = (float*)base;
-  float* ring[3] = {(float*)(base + vol_b), (float*)(base + 2 * vol_b), (float*)(base + 3 * vol_b)};
-  float* lw = (float*)(base + 4 * vol_b);          // A,B,C,D contiguous (vol_b is 256-aligned)
-  // log_scale_impl strides its work area by Z*Y*pitch floats, which fits in vol_b each
-  char* tail = base + 8 * vol_b;
-  mmb_cand* cand2 = (mmb_cand*)tail;
-  uint8_t* keep = (uint8_t*)(tail + align256((int64_t)capacity * (int64_t)sizeof(mmb_cand)));
-  int* counter = (int*)((char*)keep + align256(capacity));
+  float* ring[3] = {(float*)(base + L.vol_b), (float*)(base + 2 * L.vol_b),
+                    (float*)(base + 3 * L.vol_b)};
+  float* lw = (float*)(base + 4 * L.vol_b);       // A,B,C,D (log_scale_impl strides by Z*Y*pitch)
+  char* tail = base + 8 * L.vol_b;
+  mmb_cand* cand2 = (mmb_cand*)tail;                    tail += L.cand_b;
+  uint8_t* keep = (uint8_t*)tail;                       tail += L.keep_b;
+  int2* edges = (int2*)tail;                            tail += L.edges_b;
+  unsigned char* state = (unsigned char*)tail;          tail += L.state_b;
+  int* counters = (int*)tail;      // [0] peaks, [1] survivors, [2] edges
 
-  int rc;
   if (pre) rc = preprocess_impl(in, dtype, in_strides, Z, Y, X, bz, by, bx, pre, F, pitch, st);
   else rc = to_float_impl(in, dtype, in_strides, Z, Y, X, F, pitch, scale, st);
   if (rc) return rc;
 
-  MMB_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
+  MMB_CHECK_CUDA(cudaMemsetAsync(counters, 0, 3 * sizeof(int), st));
   const float thr = (float)threshold;
   // ring slot of scale i is i % 3; local maxima of scale i-1 run once scale i exists
   for (int i = 0; i < num_sigma; ++i) {
@@ -141,7 +220,7 @@ extern "C" int mmb_detect_chunk(const void* in, int dtype, const int64_t in_stri
     if (i >= 1) {
       const float* prev = i >= 2 ? ring[(i - 2) % 3] : nullptr;
       rc = localmax_impl(prev, ring[(i - 1) % 3], ring[i % 3], Z, Y, X, pitch, i - 1, thr, z_lo,
-                         z_hi, cand2, capacity, counter, st);
+                         z_hi, cand2, capacity, counters, st);
       if (rc) return rc;
     }
   }
@@ -149,28 +228,54 @@ extern "C" int mmb_detect_chunk(const void* in, int dtype, const int64_t in_stri
     const int i = num_sigma - 1;
     const float* prev = i >= 1 ? ring[(i - 1) % 3] : nullptr;
     rc = localmax_impl(prev, ring[i % 3], nullptr, Z, Y, X, pitch, i, thr, z_lo, z_hi, cand2,
-                       capacity, counter, st);
+                       capacity, counters, st);
     if (rc) return rc;
   }
-  int n = 0;
-  MMB_CHECK_CUDA(cudaMemcpyAsync(&n, counter, sizeof(int), cudaMemcpyDeviceToHost, st));
-  MMB_CHECK_CUDA(cudaStreamSynchronize(st));
-  if (n_peaks) *n_peaks = n;
-  if (n > capacity) {
-    set_error("candidate buffer overflow: %d local maxima, capacity %d", n, capacity);
-    *n_out = n;
-    return MMB_ERR_OVERFLOW;
-  }
-  if (n == 0) { *n_out = 0; return MMB_OK; }
-  rc = prune_within_impl(cand2, n, sigmas, num_sigma, overlap, Y, X, keep, st);
+  rc = prune_within_enqueue(cand2, counters, capacity, ladder, overlap, Y, X, edges, L.edge_cap,
+                            counters + 2, state, keep, st);
   if (rc) return rc;
-  MMB_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
   {
-    ProfScope ps(PROF_COMPACT, n, st);
-    compact_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(cand2, keep, n, cand, counter);
+    ProfScope ps(PROF_COMPACT, capacity, st);
+    compact_kernel<<<(unsigned)cdiv(capacity, 256), 256, 0, st>>>(cand2, keep, counters, capacity,
+                                                                  cand, counters + 1);
   }
   MMB_CHECK_LAUNCH();
-  MMB_CHECK_CUDA(cudaMemcpyAsync(n_out, counter, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MMB_CHECK_CUDA(cudaMemcpyAsync(status, counters, 3 * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  return MMB_OK;
+}
+
+extern "C" int mmb_detect_edge_capacity(int capacity) { return 4 * capacity + 4096; }
+
+extern "C" int mmb_detect_chunk(const void* in, int dtype, const int64_t in_strides[3], int Z,
+                                int Y, int X, int64_t pitch, double scale,
+                                const mmb_preproc_params* pre, int bz, int by, int bx,
+                                const double* sigmas, int num_sigma, double threshold,
+                                double overlap, int z_lo, int z_hi, void* work, mmb_cand* cand,
+                                int capacity, int* n_out, int* n_peaks, void* stream) {
+  MMB_REQUIRE(n_out, "null buffer");
+  MMB_REQUIRE(work && capacity > 0 && Z > 0 && Y > 0 && pitch > 0, "bad workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  const ChunkLayout L = chunk_layout(Z, Y, pitch, capacity);
+  // the driver's own counter block doubles as the status block of the synchronous form
+  int32_t* status = (int32_t*)((char*)work + L.total - 256) + 8;
+  int rc = mmb_detect_chunk_enqueue(in, dtype, in_strides, Z, Y, X, pitch, scale, pre, bz, by, bx,
+                                    sigmas, num_sigma, threshold, overlap, z_lo, z_hi, work, cand,
+                                    capacity, status, stream);
+  if (rc) return rc;
+  int32_t host[3] = {0, 0, 0};
+  MMB_CHECK_CUDA(cudaMemcpyAsync(host, status, sizeof(host), cudaMemcpyDeviceToHost, st));
   MMB_CHECK_CUDA(cudaStreamSynchronize(st));
+  if (n_peaks) *n_peaks = host[0];
+  if (host[0] > capacity) {
+    set_error("candidate buffer overflow: %d local maxima, capacity %d", host[0], capacity);
+    *n_out = host[0];
+    return MMB_ERR_OVERFLOW;
+  }
+  if (host[2] > L.edge_cap) {
+    set_error("kill-edge buffer overflow: %d edges, capacity %d", host[2], L.edge_cap);
+    *n_out = (host[2] - 4096) / 4 + 1;        // capacity whose edge buffer would fit
+    return MMB_ERR_OVERFLOW;
+  }
+  *n_out = host[1];
   return MMB_OK;
 }

@@ -62,6 +62,16 @@ int gaussian_radius(double sigma);
 // fills w (zero beyond r); returns r or -1 if r > kMaxRadius
 int make_log_weights(double sigma, LogWeights* w);
 
+// the sigma ladder travels in kernel parameter space (no device allocation, no
+// host-buffer lifetime to manage on the asynchronous path)
+constexpr int kMaxSigmas = 64;
+struct SigmaLadder {
+  double s[kMaxSigmas];
+  int n;
+};
+
+int num_sms();   // SM count of the current device (cached)
+
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // Optional per-kernel timing with CUDA events on the launching stream

@@ -10,18 +10,21 @@
 
 namespace mmb {
 
-// A CTA owns an 8-row x 512-column tile of one z-plane of scale `cur`, staged in
-// shared memory with a one-voxel halo ('nearest' = clamped indices at the faces).
-// Every thread owns four consecutive x (16-byte loads).  Cold voxels cost a
-// quarter of a load and a quarter of a shared store each.  An above-threshold
-// voxel is first tested against its eight in-plane neighbours from shared memory;
-// the few 2-D maxima that survive (about one per blob per plane) are then tested
-// against the two neighbouring planes and the 54 voxels of the adjacent scales
-// with global loads.
+// A warp owns an 8-row x 128-column strip of one z-plane of scale `cur`; every
+// thread owns four consecutive x and keeps its 10 rows (8 + one halo row above
+// and below, 'nearest' = clamped row indices) in registers: ten 16-byte loads in
+// flight per thread, no shared memory.  The in-plane 3x3 maximum is separable:
+// a vertical max of three rows per column, then a horizontal max of three
+// columns, with the two columns next to a thread's four taken from the
+// neighbouring lanes by shuffle (lanes 0 and 31 only carry those columns for
+// lanes 1 and 30, so a warp emits 120 of the 128 columns it loads).  Cold voxels cost about seven instructions each.  The few in-plane
+// maxima above threshold (about one per blob per plane) are then tested against
+// the two neighbouring planes and the 54 voxels of the adjacent scales with
+// global loads.
 constexpr int kLmThreads = 128;
-constexpr int kLmRows = 8;
-constexpr int kLmCols = kLmThreads * 4;
-constexpr int kLmPitch = kLmCols + 8;        // data starts at column 4 (keeps float4 alignment)
+constexpr int kLmRows = 8;                     // rows per warp
+constexpr int kLmWarps = kLmThreads / 32;
+constexpr int kLmCols = 120;                   // output columns per warp: 30 lanes x 4
 
 __device__ __forceinline__ bool row_beats(const float* __restrict__ row, int xl, int x, int xr,
                                           float v) {
@@ -29,7 +32,7 @@ __device__ __forceinline__ bool row_beats(const float* __restrict__ row, int xl,
 }
 
 // planes z-1, z+1 of the same scale and all 27 voxels of each adjacent scale
-__device__ bool survives_3d_and_scales(const float* __restrict__ prev,
+__device__ __noinline__ bool survives_3d_and_scales(const float* __restrict__ prev,
                                        const float* __restrict__ cur,
                                        const float* __restrict__ next, int Z, int Y, int X,
                                        int64_t pitch, int z, int y, int x, float v) {
@@ -54,58 +57,72 @@ __device__ bool survives_3d_and_scales(const float* __restrict__ prev,
   return true;
 }
 
-__global__ void __launch_bounds__(kLmThreads)
+__global__ void __launch_bounds__(kLmThreads, 6)
 localmax_kernel(const float* __restrict__ prev, const float* __restrict__ cur,
                 const float* __restrict__ next, int Z, int Y, int X, int64_t pitch, int s,
                 float thr, int z_lo, int z_hi, mmb_cand* __restrict__ out, int capacity,
                 int* __restrict__ counter) {
-  __shared__ __align__(16) float tile[(kLmRows + 2) * kLmPitch];
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int z = z_lo + blockIdx.z;
-  const int y0 = blockIdx.y * kLmRows;
-  const int xt = blockIdx.x * kLmCols;          // first column of the tile
-  const int x0 = xt + tid * 4;
+  const int y0 = (blockIdx.y * kLmWarps + warp) * kLmRows;
+  if (y0 >= Y) return;                                  // warp-uniform
+  // lanes 1..30 own outputs; lanes 0 and 31 only carry the neighbouring columns
+  const int x0 = blockIdx.x * kLmCols - 4 + lane * 4;
   const float* plane = cur + (int64_t)z * Y * pitch;
+  const float NEG = -INFINITY;
+
+  // rows y0-1 .. y0+8 (clamped row indices = 'nearest'); everything outside the
+  // volume is -inf so it never wins a maximum
+  float4 v[kLmRows + 2];
 #pragma unroll
   for (int rr = 0; rr < kLmRows + 2; ++rr) {
     const int y = min(max(y0 - 1 + rr, 0), Y - 1);
-    const float* row = plane + (int64_t)y * pitch;
-    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (x0 < X) q = __ldg(reinterpret_cast<const float4*>(row + x0));
-    *reinterpret_cast<float4*>(&tile[rr * kLmPitch + 4 + tid * 4]) = q;
-    if (tid == 0) tile[rr * kLmPitch + 3] = xt > 0 ? __ldg(row + xt - 1) : 0.f;
-    if (tid == 1) tile[rr * kLmPitch + 4 + kLmCols] = xt + kLmCols < X ? __ldg(row + xt + kLmCols) : 0.f;
+    v[rr] = make_float4(NEG, NEG, NEG, NEG);
+    if (x0 >= 0 && x0 < X)
+      v[rr] = __ldg(reinterpret_cast<const float4*>(plane + (int64_t)y * pitch + x0));
   }
-  __syncthreads();
-#pragma unroll 1
+  // columns past X inside a loaded float4 hold row padding: mask them
+  if (x0 + 3 >= X) {
+#pragma unroll
+    for (int rr = 0; rr < kLmRows + 2; ++rr) {
+      if (x0 + 1 >= X) v[rr].y = NEG;
+      if (x0 + 2 >= X) v[rr].z = NEG;
+      if (x0 + 3 >= X) v[rr].w = NEG;
+    }
+  }
+  const bool owner = lane >= 1 && lane <= 30;
+
+#pragma unroll
   for (int r = 1; r <= kLmRows; ++r) {
     const int y = y0 + r - 1;
-    const bool row_ok = y < Y;                         // uniform across the CTA
-    const float* t = &tile[r * kLmPitch + 4 + tid * 4];
-    const float4 q = *reinterpret_cast<const float4*>(t);
-    const float vs[4] = {q.x, q.y, q.z, q.w};
-    unsigned hot = 0;
+    if (y >= Y) break;                                   // warp-uniform
+    // vertical maxima of rows r-1, r, r+1
+    const float c0 = fmaxf(fmaxf(v[r - 1].x, v[r].x), v[r + 1].x);
+    const float c1 = fmaxf(fmaxf(v[r - 1].y, v[r].y), v[r + 1].y);
+    const float c2 = fmaxf(fmaxf(v[r - 1].z, v[r].z), v[r + 1].z);
+    const float c3 = fmaxf(fmaxf(v[r - 1].w, v[r].w), v[r + 1].w);
+    const float cl = __shfl_up_sync(0xffffffffu, c3, 1);
+    const float cr = __shfl_down_sync(0xffffffffu, c0, 1);
+    // 3x3 maxima (the centre is included, so "is a maximum" is !(m > v))
+    const float m0 = fmaxf(fmaxf(cl, c0), c1);
+    const float m1 = fmaxf(fmaxf(c0, c1), c2);
+    const float m2 = fmaxf(fmaxf(c1, c2), c3);
+    const float m3 = fmaxf(fmaxf(c2, c3), cr);
+    const float vs[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
+    const float ms[4] = {m0, m1, m2, m3};
+    unsigned cand = 0;
+    if (owner) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (row_ok && x0 + k < X && vs[k] > thr) hot |= 1u << k;
-    if (!__any_sync(0xffffffffu, hot != 0)) continue;
+      for (int k = 0; k < 4; ++k)
+        if (vs[k] > thr && !(ms[k] > vs[k])) cand |= 1u << k;
+    }
+    if (!__any_sync(0xffffffffu, cand != 0)) continue;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
+      if (!__any_sync(0xffffffffu, (cand >> k) & 1u)) continue;
       bool peak = false;
-      if (hot & (1u << k)) {
-        const int x = x0 + k;
-        const float v = vs[k];
-        // clamped in-tile neighbour columns ('nearest' at the x faces)
-        const int cl = x > 0 ? k - 1 : k, cr = x < X - 1 ? k + 1 : k;
-        // rows r-1 / r+1 already hold clamped y (loaded with clamped indices)
-        const float* up = t - kLmPitch;
-        const float* dn = t + kLmPitch;
-        float m = fmaxf(t[cl], t[cr]);
-        m = fmaxf(m, fmaxf(fmaxf(up[cl], up[k]), up[cr]));
-        m = fmaxf(m, fmaxf(fmaxf(dn[cl], dn[k]), dn[cr]));
-        peak = !(m > v);
-        if (peak) peak = survives_3d_and_scales(prev, cur, next, Z, Y, X, pitch, z, y, x, v);
-      }
+      if (cand & (1u << k))
+        peak = survives_3d_and_scales(prev, cur, next, Z, Y, X, pitch, z, y, x0 + k, vs[k]);
       const unsigned ballot = __ballot_sync(0xffffffffu, peak);
       if (ballot) {
         int base = 0;
@@ -135,7 +152,7 @@ int localmax_impl(const float* prev, const float* cur, const float* next, int Z,
   const int nz = z_hi - z_lo;
   for (int zb = 0; zb < nz; zb += 65535) {
     const int zn = nz - zb < 65535 ? nz - zb : 65535;
-    dim3 grid((unsigned)cdiv(X, kLmCols), (unsigned)cdiv(Y, kLmRows), (unsigned)zn);
+    dim3 grid((unsigned)cdiv(X, kLmCols), (unsigned)cdiv(Y, kLmRows * kLmWarps), (unsigned)zn);
     ProfScope ps(PROF_LOCALMAX, (double)zn * Y * X, st);
     localmax_kernel<<<grid, kLmThreads, 0, st>>>(prev, cur, next, Z, Y, X, pitch, s, thr,
                                                  z_lo + zb, z_hi, out, capacity, counter);
@@ -152,7 +169,7 @@ extern "C" int mmb_localmax_compact(const float* prev, const float* cur, const f
                                     int* counter, void* stream) {
   MMB_REQUIRE(cur && out && counter, "null buffer");
   MMB_REQUIRE(Z > 0 && Y > 0 && X > 0 && pitch >= X, "bad shape");
-  MMB_REQUIRE(Y <= 65535 * 8, "Y too large");
+  MMB_REQUIRE(Y <= 65535 * 32, "Y too large");
   MMB_REQUIRE(z_lo >= 0 && z_hi <= Z, "bad z range");
   MMB_REQUIRE(capacity >= 0, "bad capacity");
   return mmb::localmax_impl(prev, cur, next, Z, Y, X, pitch, s, thr, z_lo, z_hi, out, capacity,

@@ -9,13 +9,14 @@
 //     unsharp: x + (x - strength * gaussian(x, sigma=8, mode='nearest'));
 //     octahedron(1) erosion when mean > erosion_threshold.
 // The block lives in shared memory for the whole pipeline: exact order
-// statistics by an 8-bit MSB radix select over order-preserving float keys (both
+// statistics by bisection over the key bits with the keys held in registers (both
 // percentiles in the same passes), float64 for the percentile interpolation, the
 // stretch and the block mean (they feed equality / threshold decisions), then the
 // sigma=8 blur as three in-place matrix sweeps (radius 32 exceeds the block, so
 // with 'nearest' padding each 1-D pass is a dense n x n matrix built on the
 // host), unsharp, erosion, and one write of float32.
 #include <math.h>
+#include <type_traits>
 #include <vector>
 #include <map>
 #include <mutex>
@@ -24,6 +25,7 @@
 namespace mmb {
 
 constexpr int kPreThreads = 640;
+constexpr int kPreMinBlocks = 2;
 
 struct PreGeom {
   int Z, Y, X;
@@ -47,11 +49,14 @@ __device__ __forceinline__ double np_lerp(double a, double b, double t) {
   return t >= 0.5 ? b - d * (1.0 - t) : a + d * t;
 }
 
-template <typename T, int NL>
-__global__ void __launch_bounds__(kPreThreads)
-preprocess_kernel(const T* __restrict__ in, PreGeom g, mmb_preproc_params p,
-                  const float* __restrict__ mats, int mat_pitch,
-                  float* __restrict__ out) {
+// FULL: the block is NL x NL x NL, so every index decomposition divides by a
+// compile-time constant; partial blocks at the chunk faces take the generic body.
+template <typename T, int NL, bool FULL>
+__device__ __forceinline__ void preprocess_body(const T* __restrict__ in, const PreGeom& g,
+                                                const mmb_preproc_params& p,
+                                                const float* __restrict__ mats, int mat_pitch,
+                                                float* __restrict__ out, int z0, int y0, int x0,
+                                                int nz_rt, int ny_rt, int nx_rt) {
   constexpr int NVOX = NL * NL * NL;
   constexpr int NPT = (NVOX + kPreThreads - 1) / kPreThreads;
   constexpr int NVOXP = (NVOX + 3) / 4 * 4;      // keeps M 16-byte aligned for float4 rows
@@ -70,12 +75,7 @@ preprocess_kernel(const T* __restrict__ in, PreGeom g, mmb_preproc_params p,
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  int b = blockIdx.x;
-  const int bxi = b % g.nbx; b /= g.nbx;
-  const int byi = b % g.nby; b /= g.nby;
-  const int bzi = b;
-  const int z0 = bzi * g.bz, y0 = byi * g.by, x0 = bxi * g.bx;
-  const int nz = min(g.bz, g.Z - z0), ny = min(g.by, g.Y - y0), nx = min(g.bx, g.X - x0);
+  const int nz = FULL ? NL : nz_rt, ny = FULL ? NL : ny_rt, nx = FULL ? NL : nx_rt;
   const int n = nz * ny * nx;
   const int nyx = ny * nx;
 
@@ -107,79 +107,66 @@ preprocess_kernel(const T* __restrict__ in, PreGeom g, mmb_preproc_params p,
   }
   __syncthreads();
 
-  // ---- radix select of ranks s_k[0], s_k[1] --------------------------------
-  unsigned mask = 0u;
-  const int n_round = (n + 31) / 32 * 32;
-  for (int pass = 3; pass >= 0; --pass) {
-    const int shift = pass * 8;
-    for (int i = tid; i < 512; i += kPreThreads) hist[i] = 0;
-    __syncthreads();
-    const unsigned pf0 = s_prefix[0], pf1 = s_prefix[1];
-    for (int i = tid; i < n_round; i += kPreThreads) {
-      unsigned key = 0u;
-      const bool inb = i < n;
-      if (inb) key = key_of(vals[i]);
-      const int bin = (key >> shift) & 255;
+  // ---- exact order statistics of ranks s_k[0], s_k[1] ---------------------------
+  // Bisection over the key bits, most significant first: K grows to the largest
+  // value with count(key < K) <= rank, which is the element of that rank.  Every
+  // thread keeps the keys of its voxels in registers, so a pass is NPT compares
+  // per percentile, one warp reduction and one barrier - no shared-memory
+  // histogram, no atomics.  Integer inputs need only as many passes as they have
+  // bits (16 for uint16); floats use the order-preserving 32-bit key.
+  constexpr bool INTKEY = std::is_integral<T>::value;
+  constexpr int NBITS = INTKEY ? 8 * (int)sizeof(T) : 32;
+  constexpr int NW = kPreThreads / 32;
+  unsigned keys[NPT];
 #pragma unroll
-      for (int w = 0; w < 2; ++w) {
-        const bool valid = inb && ((key & mask) == (w == 0 ? pf0 : pf1));
-        const unsigned act = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-          const unsigned peers = __match_any_sync(act, bin);
-          if (lane == __ffs(peers) - 1) atomicAdd(&hist[w * 256 + bin], __popc(peers));
-        }
+  for (int k = 0; k < NPT; ++k) {
+    const int i = tid + k * kPreThreads;
+    keys[k] = 0xffffffffu;                    // padding never counts as "< K"
+    if (i < n) keys[k] = INTKEY ? (unsigned)vals[i] : key_of(vals[i]);
+  }
+  unsigned K0 = 0u, K1 = 0u;
+  {
+    const int k0 = s_k[0], k1 = s_k[1];
+#pragma unroll 1
+    for (int bit = NBITS - 1; bit >= 0; --bit) {
+      const unsigned T0 = K0 | (1u << bit), T1 = K1 | (1u << bit);
+      int c0 = 0, c1 = 0;
+#pragma unroll
+      for (int k = 0; k < NPT; ++k) {
+        c0 += keys[k] < T0 ? 1 : 0;
+        c1 += keys[k] < T1 ? 1 : 0;
       }
+      c0 = __reduce_add_sync(0xffffffffu, c0);
+      c1 = __reduce_add_sync(0xffffffffu, c1);
+      int* slot = hist + (bit & 1) * 2 * NW;   // double-buffered: one barrier per pass
+      if (lane == 0) { slot[warp] = c0; slot[NW + warp] = c1; }
+      __syncthreads();
+      int t0 = lane < NW ? slot[lane] : 0;
+      int t1 = lane < NW ? slot[NW + lane] : 0;
+      t0 = __reduce_add_sync(0xffffffffu, t0);
+      t1 = __reduce_add_sync(0xffffffffu, t1);
+      if (t0 <= k0) K0 = T0;
+      if (t1 <= k1) K1 = T1;
     }
-    __syncthreads();
-    if (warp < 2) {
-      // warp w scans its 256-bin histogram: 8 bins per lane
-      const int* h = hist + warp * 256;
-      int loc[8];
-      int sum = 0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { loc[j] = h[lane * 8 + j]; sum += loc[j]; }
-      int incl = sum;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-      }
-      const int excl = incl - sum;
-      const int k = s_k[warp];
-      const bool has = k >= excl && k < incl;      // exactly one lane
-      if (has) {
-        int acc = excl, bsel = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (k >= acc && k < acc + loc[j]) { bsel = j; break; }
-          acc += loc[j];
-        }
-        s_k[warp] = k - acc;
-        s_prefix[warp] |= (unsigned)(lane * 8 + bsel) << shift;
-      }
-    }
-    mask |= 255u << shift;
-    __syncthreads();
   }
   // successor of each selected value: count(key <= K) and min(key > K)
   {
-    if (tid < 2) { s_cnt_le[tid] = 0; s_next[tid] = 0xffffffffu; }
+    if (tid < 2) { s_cnt_le[tid] = 0; s_next[tid] = 0xffffffffu; s_prefix[tid] = tid == 0 ? K0 : K1; }
     __syncthreads();
-    const unsigned K0 = s_prefix[0], K1 = s_prefix[1];
     int c0 = 0, c1 = 0;
     unsigned m0 = 0xffffffffu, m1 = 0xffffffffu;
-    for (int i = tid; i < n; i += kPreThreads) {
-      const unsigned key = key_of(vals[i]);
-      if (key <= K0) ++c0; else m0 = min(m0, key);
-      if (key <= K1) ++c1; else m1 = min(m1, key);
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      c0 += __shfl_xor_sync(0xffffffffu, c0, o);
-      c1 += __shfl_xor_sync(0xffffffffu, c1, o);
-      m0 = min(m0, __shfl_xor_sync(0xffffffffu, m0, o));
-      m1 = min(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+    for (int k = 0; k < NPT; ++k) {
+      if (tid + k * kPreThreads < n) {
+        const unsigned key = keys[k];
+        if (key <= K0) ++c0; else m0 = min(m0, key);
+        if (key <= K1) ++c1; else m1 = min(m1, key);
+      }
     }
+    c0 = __reduce_add_sync(0xffffffffu, c0);
+    c1 = __reduce_add_sync(0xffffffffu, c1);
+    m0 = __reduce_min_sync(0xffffffffu, m0);
+    m1 = __reduce_min_sync(0xffffffffu, m1);
     if (lane == 0) {
       atomicAdd(&s_cnt_le[0], c0); atomicAdd(&s_cnt_le[1], c1);
       atomicMin(&s_next[0], m0);   atomicMin(&s_next[1], m1);
@@ -192,14 +179,15 @@ preprocess_kernel(const T* __restrict__ in, PreGeom g, mmb_preproc_params p,
       const double q = (w == 0 ? p.clip_vmin : p.clip_vmax) / 100.0;
       const double virt = (double)(n - 1) * q;
       double prev = floor(virt);
-      const double a = (double)float_of(s_prefix[w]);
+      const double a = INTKEY ? (double)s_prefix[w] : (double)float_of(s_prefix[w]);
       double bb = a;
       double gamma = virt - prev;
       if (virt >= (double)(n - 1) || virt < 0.0) {
         gamma = 0.0;                       // both neighbours are the same sample
       } else {
         const int k = (int)prev;           // rank of a; rank k+1 is a again if duplicated
-        if (k + 1 >= s_cnt_le[w]) bb = (double)float_of(s_next[w]);
+        if (k + 1 >= s_cnt_le[w])
+          bb = INTKEY ? (double)s_next[w] : (double)float_of(s_next[w]);
       }
       v[w] = np_lerp(a, bb, gamma);
     }
@@ -306,6 +294,23 @@ preprocess_kernel(const T* __restrict__ in, PreGeom g, mmb_preproc_params p,
       out[((int64_t)(z0 + z) * g.Y + (y0 + y)) * g.pitch + (x0 + x)] = v;
     }
   }
+}
+
+template <typename T, int NL>
+__global__ void __launch_bounds__(kPreThreads, NL <= 25 ? kPreMinBlocks : 1)
+preprocess_kernel(const T* __restrict__ in, const __grid_constant__ PreGeom g,
+                  const __grid_constant__ mmb_preproc_params p, const float* __restrict__ mats,
+                  int mat_pitch, float* __restrict__ out) {
+  int b = blockIdx.x;
+  const int bxi = b % g.nbx; b /= g.nbx;
+  const int byi = b % g.nby; b /= g.nby;
+  const int bzi = b;
+  const int z0 = bzi * g.bz, y0 = byi * g.by, x0 = bxi * g.bx;
+  const int nz = min(g.bz, g.Z - z0), ny = min(g.by, g.Y - y0), nx = min(g.bx, g.X - x0);
+  if (nz == NL && ny == NL && nx == NL)       // CTA-uniform
+    preprocess_body<T, NL, true>(in, g, p, mats, mat_pitch, out, z0, y0, x0, nz, ny, nx);
+  else
+    preprocess_body<T, NL, false>(in, g, p, mats, mat_pitch, out, z0, y0, x0, nz, ny, nx);
 }
 
 // dense matrices of scipy.ndimage.gaussian_filter1d(sigma=8, truncate=4,

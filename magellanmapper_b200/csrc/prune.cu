@@ -55,10 +55,18 @@ constexpr int kTile = 256;
 
 // all pairs i < j, tile of j staged in shared memory; emits (killer, victim)
 __global__ void __launch_bounds__(kTile)
-prune_edges_kernel(const mmb_cand* __restrict__ cand, int n, const double* __restrict__ sigmas,
-                   int num_sigma, double overlap, int Y, int X, int2* __restrict__ edges,
-                   int edge_cap, int* __restrict__ edge_count) {
+prune_edges_kernel(const mmb_cand* __restrict__ cand, const int* __restrict__ n_ptr, int n_max,
+                   const __grid_constant__ SigmaLadder ladder, double overlap, int Y, int X,
+                   int2* __restrict__ edges, int edge_cap, int* __restrict__ edge_count) {
   __shared__ mmb_cand tile[kTile];
+  __shared__ double sigmas[kMaxSigmas];
+  // the candidate count lives on the device (no host round trip); the grid is
+  // sized for the buffer capacity and surplus CTAs leave at once
+  const int n = min(*n_ptr, n_max);
+  if (blockIdx.x * kTile >= n) return;
+  const int num_sigma = ladder.n;
+  for (int k = threadIdx.x; k < num_sigma; k += kTile) sigmas[k] = ladder.s[k];
+  __syncthreads();
   const int i = blockIdx.x * kTile + threadIdx.x;
   mmb_cand me;
   me.z = me.y = me.x = 0; me.s = 0; me.resp = 0.f;
@@ -105,10 +113,13 @@ prune_edges_kernel(const mmb_cand* __restrict__ cand, int n, const double* __res
 
 // single-CTA fixed point over the kill graph. state: 0 unknown, 1 alive, 2 dead
 __global__ void __launch_bounds__(1024)
-prune_resolve_kernel(int n, const int2* __restrict__ edges, int n_edges,
+prune_resolve_kernel(const int* __restrict__ n_ptr, int n_max, const int2* __restrict__ edges,
+                     const int* __restrict__ n_edges_ptr, int edge_cap,
                      unsigned char* __restrict__ state, unsigned char* __restrict__ mark,
                      unsigned char* __restrict__ keep) {
   __shared__ int remaining;
+  const int n = min(*n_ptr, n_max);
+  const int n_edges = min(*n_edges_ptr, edge_cap);
   for (int v = threadIdx.x; v < n; v += blockDim.x) state[v] = 0;
   __syncthreads();
   while (true) {
@@ -142,51 +153,74 @@ prune_resolve_kernel(int n, const int2* __restrict__ edges, int n_edges,
   for (int v = threadIdx.x; v < n; v += blockDim.x) keep[v] = state[v] == 1 ? 1 : 0;
 }
 
+int make_ladder(const double* sigmas_host, int num_sigma, SigmaLadder* out) {
+  if (num_sigma < 1 || num_sigma > kMaxSigmas) {
+    set_error("num_sigma %d outside 1..%d", num_sigma, kMaxSigmas);
+    return MMB_ERR_UNSUPPORTED;
+  }
+  out->n = num_sigma;
+  for (int k = 0; k < kMaxSigmas; ++k) out->s[k] = k < num_sigma ? sigmas_host[k] : 0.0;
+  return MMB_OK;
+}
+
+// Fully asynchronous pruning of the first min(*n_ptr, n_max) candidates.  Scratch is
+// caller-provided: edges[edge_cap], edge_count (1 int), state[2 * (n_max + 8)] bytes.
+// *edge_count may exceed edge_cap afterwards: the caller must check and redo.
+int prune_within_enqueue(const mmb_cand* cand, const int* n_ptr, int n_max,
+                         const SigmaLadder& ladder, double overlap, int Y, int X, int2* edges,
+                         int edge_cap, int* edge_count, unsigned char* state, uint8_t* keep,
+                         cudaStream_t st) {
+  if (n_max <= 0) return MMB_OK;
+  const int64_t npad = (n_max + 3) / 4 * 4 + 4;
+  MMB_CHECK_CUDA(cudaMemsetAsync(edge_count, 0, sizeof(int), st));
+  {
+    ProfScope ps(PROF_PRUNE_EDGES, n_max, st);
+    prune_edges_kernel<<<(unsigned)cdiv(n_max, kTile), kTile, 0, st>>>(
+        cand, n_ptr, n_max, ladder, overlap, Y, X, edges, edge_cap, edge_count);
+  }
+  MMB_CHECK_LAUNCH();
+  {
+    ProfScope ps(PROF_PRUNE_RESOLVE, n_max, st);
+    prune_resolve_kernel<<<1, 1024, 0, st>>>(n_ptr, n_max, edges, edge_count, edge_cap, state,
+                                             state + npad, keep);
+  }
+  MMB_CHECK_LAUNCH();
+  return MMB_OK;
+}
+
 int prune_within_impl(const mmb_cand* cand, int n, const double* sigmas_host, int num_sigma,
                       double overlap, int Y, int X, uint8_t* keep, cudaStream_t st) {
   if (n == 0) return MMB_OK;
-  double* d_sig = nullptr;
-  int* d_count = nullptr;
+  SigmaLadder ladder;
+  int rc = make_ladder(sigmas_host, num_sigma, &ladder);
+  if (rc) return rc;
+  int* d_counts = nullptr;          // [0] = n, [1] = edge count
   int2* d_edges = nullptr;
   unsigned char* d_state = nullptr;
   const int64_t npad = (n + 3) / 4 * 4 + 4;
-  MMB_CHECK_CUDA(cudaMallocAsync((void**)&d_sig, num_sigma * sizeof(double), st));
-  MMB_CHECK_CUDA(cudaMallocAsync((void**)&d_count, sizeof(int), st));
+  MMB_CHECK_CUDA(cudaMallocAsync((void**)&d_counts, 2 * sizeof(int), st));
   MMB_CHECK_CUDA(cudaMallocAsync((void**)&d_state, 2 * npad, st));
-  MMB_CHECK_CUDA(cudaMemcpyAsync(d_sig, sigmas_host, num_sigma * sizeof(double),
-                                 cudaMemcpyHostToDevice, st));
+  MMB_CHECK_CUDA(cudaMemcpyAsync(d_counts, &n, sizeof(int), cudaMemcpyHostToDevice, st));
   int edge_cap = 4 * n + 4096;
   int n_edges = 0;
   for (int attempt = 0; attempt < 2; ++attempt) {
     MMB_CHECK_CUDA(cudaMallocAsync((void**)&d_edges, (size_t)edge_cap * sizeof(int2), st));
-    MMB_CHECK_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), st));
-    {
-      ProfScope ps(PROF_PRUNE_EDGES, n, st);
-      prune_edges_kernel<<<(unsigned)cdiv(n, kTile), kTile, 0, st>>>(
-          cand, n, d_sig, num_sigma, overlap, Y, X, d_edges, edge_cap, d_count);
-    }
-    MMB_CHECK_LAUNCH();
-    MMB_CHECK_CUDA(cudaMemcpyAsync(&n_edges, d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    rc = prune_within_enqueue(cand, d_counts, n, ladder, overlap, Y, X, d_edges, edge_cap,
+                              d_counts + 1, d_state, keep, st);
+    if (rc) return rc;
+    MMB_CHECK_CUDA(cudaMemcpyAsync(&n_edges, d_counts + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
     MMB_CHECK_CUDA(cudaStreamSynchronize(st));
-    if (n_edges <= edge_cap) break;
     MMB_CHECK_CUDA(cudaFreeAsync(d_edges, st));
-    d_edges = nullptr;
+    if (n_edges <= edge_cap) break;
     edge_cap = n_edges;
   }
+  MMB_CHECK_CUDA(cudaFreeAsync(d_state, st));
+  MMB_CHECK_CUDA(cudaFreeAsync(d_counts, st));
+  MMB_CHECK_CUDA(cudaStreamSynchronize(st));
   if (n_edges > edge_cap) {
     set_error("kill-edge buffer overflow (%d > %d)", n_edges, edge_cap);
     return MMB_ERR_OVERFLOW;
   }
-  {
-    ProfScope ps(PROF_PRUNE_RESOLVE, n, st);
-    prune_resolve_kernel<<<1, 1024, 0, st>>>(n, d_edges, n_edges, d_state, d_state + npad, keep);
-  }
-  MMB_CHECK_LAUNCH();
-  MMB_CHECK_CUDA(cudaFreeAsync(d_edges, st));
-  MMB_CHECK_CUDA(cudaFreeAsync(d_state, st));
-  MMB_CHECK_CUDA(cudaFreeAsync(d_count, st));
-  MMB_CHECK_CUDA(cudaFreeAsync(d_sig, st));
-  MMB_CHECK_CUDA(cudaStreamSynchronize(st));
   return MMB_OK;
 }
 

@@ -115,6 +115,17 @@ class StackDetector(object):
         """Preprocess (per ``denoise_max_shape`` block) and detect one sub-ROI in
         ONE fused GPU call per channel, then shift the blobs to the sub-ROI's
         offset (stack_detect.py:82-172)."""
+        pending = cls.enqueue_sub_roi(coord, offset, last_coord, denoise_max_shape,
+                                      exclude_border, sub_roi, channel, coloc)
+        return cls.finish_sub_roi(pending)
+
+    @classmethod
+    def enqueue_sub_roi(cls, coord, offset, last_coord, denoise_max_shape, exclude_border,
+                        sub_roi, channel, coloc: bool = False):
+        """Launch the GPU work of one sub-ROI (every channel) without waiting
+        for it; ``finish_sub_roi`` turns the returned handle into the blob
+        table.  Splitting the two lets the table assembly of one sub-ROI
+        overlap the kernels of the next."""
         from .. import gpu
         if coloc:
             raise NotImplementedError("intensity co-localisation is outside the accelerated path")
@@ -122,7 +133,7 @@ class StackDetector(object):
         multichannel, channels = plot_3d.setup_channels(sub_roi, channel, 3)
         scale = detector.calc_scaling_factor()[2]
         det = cls._workspace(shape[:3])
-        tables = []
+        tickets = []
         for chl in channels:
             settings = config.get_roi_profile(chl)
             if settings["isotropic"] is not None:
@@ -138,10 +149,21 @@ class StackDetector(object):
                 in_scale = {gpu._lib.MMB_U8: 1 / 255.0, gpu._lib.MMB_U16: 1 / 65535.0}.get(
                     src.dtype, 1.0)
             sigmas = detector.sigma_ladder(settings, scale, f32)
-            cands, _ = det.detect(
+            if det.free_slots() == 0:
+                raise RuntimeError("no free output slot: finish a pending sub-ROI first")
+            ticket = det.enqueue(
                 src, sigmas, settings["detection_threshold"], settings["overlap"],
                 scale=in_scale, pre=pre,
                 block_shape=denoise_max_shape if denoise_max_shape is not None else (1, 1, 1))
+            tickets.append((chl, sigmas, ticket))
+        return (coord, offset, last_coord, exclude_border, shape, det, tickets)
+
+    @classmethod
+    def finish_sub_roi(cls, pending) -> Tuple[Sequence[int], Optional[np.ndarray]]:
+        coord, offset, last_coord, exclude_border, shape, det, tickets = pending
+        tables = []
+        for chl, sigmas, ticket in tickets:
+            cands, _ = det.collect(ticket)
             if len(cands):
                 tables.append(detector.cands_to_blobs(cands, sigmas, shape[1:3], chl))
         segments = np.vstack(tables) if tables else None
@@ -160,7 +182,10 @@ class StackDetector(object):
                               denoise_max_shape, exclude_border, coloc, channel):
         """Run every sub-ROI through the GPU in z, y, x order and collect the
         blob tables in an object array shaped like the chunk grid
-        (stack_detect.py:175-257)."""
+        (stack_detect.py:175-257).  The reference fans out over a process pool;
+        here sub-ROIs are enqueued back to back on one stream and their tables
+        are assembled on the host while later sub-ROIs compute."""
+        from collections import deque
         from .. import gpu
         last_coord = np.subtract(sub_roi_slices.shape, 1)
         # a host image that fits is moved to the device once (one large DMA, fast
@@ -172,11 +197,25 @@ class StackDetector(object):
         seg_rois = np.zeros(sub_roi_slices.shape, dtype=object)
         # size the workspace once for the largest chunk
         largest = [max(s[a].stop - s[a].start for s in sub_roi_slices.flat) for a in range(3)]
-        cls._workspace(tuple(largest))
-        for coord in np.ndindex(*sub_roi_slices.shape):
-            _, segments = cls.detect_sub_roi_from_data(
-                coord, sub_roi_slices[coord], sub_rois_offsets[coord])
+        det = cls._workspace(tuple(largest))
+        n_chl = len(plot_3d.setup_channels(img, channel, 3)[1])
+        if n_chl > det.n_slots - 1:
+            cls._gpu_detector = None
+            cls._gpu_detector = det = gpu.ChunkDetector(det.max_shape, n_slots=2 * n_chl)
+        pending = deque()
+
+        def finish_oldest():
+            coord, segments = cls.finish_sub_roi(pending.popleft())
             seg_rois[coord] = segments
+
+        for coord in np.ndindex(*sub_roi_slices.shape):
+            while pending and cls._workspace(tuple(largest)).free_slots() < n_chl:
+                finish_oldest()
+            pending.append(cls.enqueue_sub_roi(
+                coord, sub_rois_offsets[coord], last_coord, denoise_max_shape, exclude_border,
+                img[sub_roi_slices[coord]], channel, coloc))
+        while pending:
+            finish_oldest()
         # a table with zero rows is stored as None, like the reference
         for coord in np.ndindex(*seg_rois.shape):
             if seg_rois[coord] is not None and len(seg_rois[coord]) == 0:
@@ -198,9 +237,11 @@ class StackPruner(object):
         """Within one overlap slab, blobs tagged with chunk ``i`` along ``axis``
         are the masters and blobs tagged ``i + 1`` are checked against them;
         blobs of any other chunk in the slab are dropped (stack_detect.py:644-677)."""
-        blobs, axis, tol, blobs_next = pruner
+        blobs, axis, tol, n_next = pruner
         if blobs is None:
             return None, None
+        if n_next is not None and not np.isscalar(n_next):
+            n_next = len(n_next)           # the reference's tuple carries the blobs themselves
         tag_col = blobs.shape[1] - 3 + axis
         n_orig = len(blobs)
         master = blobs[blobs[:, tag_col] == i]
@@ -208,8 +249,10 @@ class StackPruner(object):
         pruned, master = detector.remove_close_blobs(check, master, tol)
         merged = np.concatenate((master, pruned))
         ratios = None
-        if blobs_next is not None:
-            ratios = detector.meas_pruning_ratio(n_orig, len(merged), len(blobs_next))
+        if n_next is not None:
+            # the reference passes the blobs of the adjacent region; only their
+            # count enters the ratio (detector.py:1122-1144)
+            ratios = detector.meas_pruning_ratio(n_orig, len(merged), n_next)
         return merged, ratios
 
     @classmethod
@@ -235,9 +278,11 @@ class StackPruner(object):
                 n_sec = sub_rois_offsets.shape[axis]
                 if n_sec <= 1:
                     continue
-                keep_parts = []
+                # row selections are kept as index arrays over a contiguous copy of
+                # the coordinate column; the wide table is gathered once per axis
+                pos = np.ascontiguousarray(blobs[:, axis])
+                keep_idx = []
                 work = []
-                pos = blobs[:, axis]
                 for j in range(n_sec):
                     coord = [0, 0, 0]
                     coord[axis] = j
@@ -247,22 +292,23 @@ class StackPruner(object):
                     size = sl[axis].stop - sl[axis].start
                     end = start + size
                     shift = overlap[axis] + overlap_padding[axis]
-                    blobs_ol = blobs_next = None
+                    blobs_ol = None
+                    n_next = None
                     if j < n_sec - 1:
                         lo, hi = end - shift, end + overlap_padding[axis]
-                        blobs_ol = blobs[(pos >= lo) & (pos < hi)]
+                        blobs_ol = blobs[np.flatnonzero((pos >= lo) & (pos < hi))]
                         # same-sized region just past the slab, for the ratio metric
                         nlo = end + tol[axis]
                         nhi = nlo + overlap[axis] + 2 * overlap_padding[axis]
                         total = sub_rois_offsets[last][axis] + size
                         if nlo < total and nhi < total:
-                            blobs_next = blobs[(pos >= nlo) & (pos < nhi)]
+                            n_next = int(np.count_nonzero((pos >= nlo) & (pos < nhi)))
                         upper = lo
                     else:
                         upper = end
                     lower = start + (shift if j > 0 else 0)
-                    keep_parts.append(blobs[(pos < upper) & (pos >= lower)])
-                    work.append((blobs_ol, axis, tol, blobs_next))
+                    keep_idx.append(np.flatnonzero((pos < upper) & (pos >= lower)))
+                    work.append((blobs_ol, axis, tol, n_next))
                 cls.blobs_to_prune = work
                 pruned_parts = []
                 for j in range(len(work)):
@@ -272,7 +318,7 @@ class StackPruner(object):
                     if ratios:
                         for c, v in zip(cols, ratios):
                             ratios_out.setdefault(c, []).append(v)
-                blobs = np.concatenate(keep_parts + pruned_parts)
+                blobs = np.concatenate([blobs[np.concatenate(keep_idx)]] + pruned_parts)
             per_channel.append(blobs)
         out = np.vstack(per_channel)[:, :-3]
         return out, pd.DataFrame(ratios_out)

@@ -207,52 +207,124 @@ def prune_seams(master_zyx: torch.Tensor, check_zyx: torch.Tensor, tol: Sequence
     return master_last[:nm], check_hit[:nc]
 
 
-class ChunkDetector:
-    """Reusable workspace around ``mmb_detect_chunk`` for chunks up to a
-    maximum shape (the workspace is the dominant allocation: eight float
-    volumes)."""
+class _Slot:
+    """Output buffers of one in-flight chunk: device candidates and status, and
+    their pinned host mirrors."""
 
-    def __init__(self, max_shape: Sequence[int], capacity: Optional[int] = None, device=None):
+    def __init__(self, capacity: int, device):
+        self.capacity = capacity
+        self.cand = new_cand_buffer(capacity, device)
+        self.status = torch.zeros(4, dtype=torch.int32, device=device)
+        self.status_host = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self.cand_host: Optional[torch.Tensor] = None      # pinned, grown on demand
+        self.busy = False
+
+    def host_rows(self, n: int) -> torch.Tensor:
+        if self.cand_host is None or self.cand_host.shape[0] < n:
+            rows = max(n, min(self.capacity, 65536))
+            self.cand_host = torch.empty((rows, 5), dtype=torch.int32).pin_memory()
+        return self.cand_host[:n]
+
+
+@dataclass
+class Ticket:
+    """Handle of a chunk enqueued with ``ChunkDetector.enqueue``."""
+    slot: _Slot
+    event: "torch.cuda.Event"
+    args: tuple                  # everything needed to redo the chunk after an overflow
+
+
+class ChunkDetector:
+    """Reusable workspace around ``mmb_detect_chunk_enqueue`` for chunks up to a
+    maximum shape (the workspace is the dominant allocation: eight float
+    volumes).
+
+    ``enqueue`` launches a whole chunk without any host synchronisation and
+    ``collect`` fetches its survivors later, so the host-side table assembly of
+    chunk *i* overlaps the kernels of chunk *i + 1* (the workspace is shared;
+    stream order serialises the chunks, only the small output slots rotate).
+    ``detect`` is the synchronous pair of the two."""
+
+    def __init__(self, max_shape: Sequence[int], capacity: Optional[int] = None, device=None,
+                 n_slots: int = 4):
         self.lib = _lib.load()
         self.device = device or require_cuda()
         self.max_shape = tuple(int(s) for s in max_shape)
         Z, Y, X = self.max_shape
         nvox = Z * Y * X
         self.capacity = int(capacity) if capacity else max(4096, nvox // 256)
+        self.n_slots = int(n_slots)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
         self._alloc()
 
     def _alloc(self):
         Z, Y, X = self.max_shape
         nbytes = self.lib.mmb_detect_work_bytes(Z, Y, pitch_for(X), self.capacity)
-        self.work = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
-        self.cand = new_cand_buffer(self.capacity, self.device)
+        self.work = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        # tickets in flight keep their old slots alive by reference
+        self.slots = [_Slot(self.capacity, self.device) for _ in range(self.n_slots)]
+
+    def free_slots(self) -> int:
+        return sum(not s.busy for s in self.slots)
+
+    def enqueue(self, src: Source, sigmas: Sequence[float], threshold: float, overlap: float,
+                scale: float = 1.0, pre: Optional[MmbPreprocParams] = None,
+                block_shape: Sequence[int] = (25, 25, 25), z_lo: int = 0,
+                z_hi: Optional[int] = None) -> Ticket:
+        """Launch one chunk asynchronously on the current stream."""
+        Z, Y, X = src.shape
+        if Z > self.max_shape[0] or Y > self.max_shape[1] or X > self.max_shape[2]:
+            raise ValueError(f"chunk {src.shape} exceeds workspace {self.max_shape}")
+        slot = next((s for s in self.slots if not s.busy), None)
+        if slot is None:
+            raise RuntimeError("all output slots are in flight: collect() a ticket first")
+        z_hi = Z if z_hi is None else z_hi
+        sig = (C.c_double * len(sigmas))(*[float(s) for s in sigmas])
+        bz, by, bx = (int(b) for b in block_shape)
+        _lib.check(self.lib.mmb_detect_chunk_enqueue(
+            C.c_void_p(src.ptr), src.dtype, _lib._I64x3(*src.strides), Z, Y, X, pitch_for(X),
+            float(scale), C.byref(pre) if pre is not None else None, bz, by, bx, sig,
+            len(sigmas), float(threshold), float(overlap), int(z_lo), int(z_hi),
+            _ptr(self.work), _ptr(slot.cand), slot.capacity, _ptr(slot.status), _stream()))
+        slot.status_host.copy_(slot.status, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        slot.busy = True
+        return Ticket(slot, ev, (src, sigmas, threshold, overlap, scale, pre, block_shape, z_lo,
+                                 z_hi))
+
+    def collect(self, ticket: Ticket) -> Tuple[np.ndarray, int]:
+        """Wait for a chunk; returns ``(survivors as CAND_DTYPE records, number of
+        local maxima)``.  A chunk whose candidates or kill edges overflowed the
+        buffers (counted exactly on the device) is redone once with larger ones."""
+        slot = ticket.slot
+        ticket.event.synchronize()
+        n_peaks, n_out, n_edges, _ = (int(v) for v in slot.status_host)
+        edge_cap = self.lib.mmb_detect_edge_capacity(slot.capacity)
+        if n_peaks > slot.capacity or n_edges > edge_cap:
+            slot.busy = False
+            need = max(n_peaks, (n_edges - 4096) // 4 + 1)
+            self.capacity = max(self.capacity, int(need * 1.25) + 1024)
+            self._alloc()
+            return self.detect(*ticket.args)
+        if n_out == 0:
+            slot.busy = False
+            return np.zeros(0, dtype=CAND_DTYPE), n_peaks
+        host = slot.host_rows(n_out)
+        with torch.cuda.stream(self.copy_stream):
+            host.copy_(slot.cand[:n_out], non_blocking=True)
+        self.copy_stream.synchronize()
+        out = host.numpy().view(CAND_DTYPE).reshape(-1).copy()
+        slot.busy = False
+        return out, n_peaks
 
     def detect(self, src: Source, sigmas: Sequence[float], threshold: float, overlap: float,
                scale: float = 1.0, pre: Optional[MmbPreprocParams] = None,
                block_shape: Sequence[int] = (25, 25, 25), z_lo: int = 0,
                z_hi: Optional[int] = None) -> Tuple[np.ndarray, int]:
         """Returns ``(survivors as CAND_DTYPE records, number of local maxima)``."""
-        Z, Y, X = src.shape
-        if Z > self.max_shape[0] or Y > self.max_shape[1] or X > self.max_shape[2]:
-            raise ValueError(f"chunk {src.shape} exceeds workspace {self.max_shape}")
-        z_hi = Z if z_hi is None else z_hi
-        sig = (C.c_double * len(sigmas))(*[float(s) for s in sigmas])
-        bz, by, bx = (int(b) for b in block_shape)
-        while True:
-            n_out, n_peaks = C.c_int(0), C.c_int(0)
-            rc = self.lib.mmb_detect_chunk(
-                C.c_void_p(src.ptr), src.dtype, _lib._I64x3(*src.strides), Z, Y, X, pitch_for(X),
-                float(scale), C.byref(pre) if pre is not None else None, bz, by, bx, sig,
-                len(sigmas), float(threshold), float(overlap), int(z_lo), int(z_hi),
-                _ptr(self.work), _ptr(self.cand), self.capacity, C.byref(n_out),
-                C.byref(n_peaks), _stream())
-            if rc == _lib.MMB_ERR_OVERFLOW:
-                # counted exactly: grow once to the reported size and redo the chunk
-                self.capacity = int(n_out.value * 1.25) + 1024
-                self._alloc()
-                continue
-            _lib.check(rc)
-            return cands_to_numpy(self.cand, n_out.value), n_peaks.value
+        return self.collect(self.enqueue(src, sigmas, threshold, overlap, scale, pre,
+                                         block_shape, z_lo, z_hi))
 
 
 def whole_roi_preprocess(src: Source, params: MmbPreprocParams) -> np.ndarray:
