@@ -119,6 +119,14 @@ int mmb_localmax_compact(const float* prev, const float* cur, const float* next,
 int mmb_prune_within(const mmb_cand* cand, int n, const double* sigmas,
                      int num_sigma, double overlap, int Y, int X,
                      uint8_t* keep, void* stream);
+/* Same result for candidates listed by ascending z: the pair search then stops
+ * at the cut-off distance 2*sigma_max*sqrt(3)+1 in z instead of visiting all
+ * pairs.  Used for the single prune over the gathered candidates of every
+ * z-slab in the seamless multi-GPU mode (no reference counterpart: one
+ * _prune_blobs call over the whole volume, detector.py:931).                 */
+int mmb_prune_within_zsorted(const mmb_cand* cand, int n, const double* sigmas,
+                             int num_sigma, double overlap, int Y, int X,
+                             uint8_t* keep, void* stream);
 
 /* ---- seam matching ------------------------------------------------------------
  * Replaces detector._find_close_blobs inside remove_close_blobs

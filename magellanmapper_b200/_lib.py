@@ -67,6 +67,8 @@ SIGNATURES = {
                                        _vp, _vp]),
     "mmb_prune_within": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_double,
                                    C.c_int, C.c_int, _vp, _vp]),
+    "mmb_prune_within_zsorted": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.c_int,
+                                           C.c_double, C.c_int, C.c_int, _vp, _vp]),
     "mmb_prune_seams": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _I32x3, _vp, _vp, _vp]),
     "mmb_detect_work_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int64, C.c_int]),
     "mmb_detect_edge_capacity": (C.c_int, [C.c_int]),

@@ -96,12 +96,12 @@ int localmax_impl(const float* prev, const float* cur, const float* next, int Z,
                   int64_t pitch, int s, float thr, int z_lo, int z_hi, mmb_cand* out,
                   int capacity, int* counter, cudaStream_t st);
 int prune_within_impl(const mmb_cand* cand, int n, const double* sigmas_host, int num_sigma,
-                      double overlap, int Y, int X, uint8_t* keep, cudaStream_t st);
+                      double overlap, int Y, int X, uint8_t* keep, cudaStream_t st, int z_sorted);
 int make_ladder(const double* sigmas_host, int num_sigma, SigmaLadder* out);
 int prune_within_enqueue(const mmb_cand* cand, const int* n_ptr, int n_max,
                          const SigmaLadder& ladder, double overlap, int Y, int X, int2* edges,
                          int edge_cap, int* edge_count, unsigned char* state, uint8_t* keep,
-                         cudaStream_t st);
+                         cudaStream_t st, int z_sorted);
 
 // stable stream compaction of the survivors to the front of a second buffer
 __global__ void compact_kernel(const mmb_cand* __restrict__ in, const uint8_t* __restrict__ keep,
@@ -232,7 +232,7 @@ extern "C" int mmb_detect_chunk_enqueue(const void* in, int dtype, const int64_t
     if (rc) return rc;
   }
   rc = prune_within_enqueue(cand2, counters, capacity, ladder, overlap, Y, X, edges, L.edge_cap,
-                            counters + 2, state, keep, st);
+                            counters + 2, state, keep, st, 0);
   if (rc) return rc;
   {
     ProfScope ps(PROF_COMPACT, capacity, st);

@@ -56,6 +56,7 @@ constexpr int kMaxRadius = 64;   // templated fast paths cover radius <= 64
 struct LogWeights {
   float g[kMaxRadius + 1];
   float h[kMaxRadius + 1];
+  float2 gh[kMaxRadius + 1];     // (g[k], h[k]) interleaved: one 64-bit constant load per tap
 };
 
 int gaussian_radius(double sigma);

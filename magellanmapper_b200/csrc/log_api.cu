@@ -32,6 +32,7 @@ int make_log_weights(double sigma, LogWeights* w) {
   for (int k = 0; k <= kMaxRadius; ++k) {
     w->g[k] = k <= r ? (float)g[k] : 0.f;
     w->h[k] = k <= r ? (float)h[k] : 0.f;
+    w->gh[k] = make_float2(w->g[k], w->h[k]);
   }
   return r;
 }

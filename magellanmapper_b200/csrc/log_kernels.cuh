@@ -21,6 +21,14 @@ namespace mmb {
 
 enum { MODE_FIRST = 0, MODE_MID = 1, MODE_LAST = 2 };
 
+// Packed FP32 FMA of sm_100 (SASS FFMA2): two independent IEEE fp32 fmas per lane
+// in one issue slot.  The sweeps are FP32-issue bound, so every inner loop below
+// is written on float2 values; ptxas folds a (w, w) or (v, v) operand into the
+// scalar-broadcast form (`UR.F32` / `R.F32`), so no register is spent on the copy.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  return __ffma2_rn(a, b, c);
+}
+
 // Convolution along a strided axis (y or z).  The volume is viewed as
 // [outer][n_axis][inner] with `inner` contiguous: (Z, Y, pitch) for the y sweep,
 // (1, Z, Y*pitch) for the z sweep.  Thread = one inner position, NB outputs.
@@ -87,17 +95,55 @@ conv_strided_kernel(const float* __restrict__ in0, const float* __restrict__ in1
   }
 }
 
+// One input row pair (v0, v1) of the strided sweeps scattered into the NB
+// accumulators it touches, then the next row: template recursion instead of a
+// loop so that every tap index is a compile-time constant whatever the unroller's
+// size heuristics decide.
+template <int R, int MODE, int NB, int COLS, int K>
+__device__ __forceinline__ void scatter_rows(const float* __restrict__ p0,
+                                             const float* __restrict__ p1, float2 (&acc0)[NB],
+                                             float2 (&acc1)[NB], const LogWeights& w) {
+  if constexpr (K < NB + 2 * R) {
+    const float2 v0 = *reinterpret_cast<const float2*>(p0 + K * COLS);
+    float2 v1 = make_float2(0.f, 0.f);
+    if (MODE != MODE_FIRST) v1 = *reinterpret_cast<const float2*>(p1 + K * COLS);
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int t = K - j;
+      if (t >= 0 && t <= 2 * R) {
+        const int wi = t >= R ? t - R : R - t;
+        const float2 g2 = make_float2(w.g[wi], w.g[wi]);
+        const float2 h2 = make_float2(w.h[wi], w.h[wi]);
+        if (MODE == MODE_FIRST) {
+          acc0[j] = ffma2(v0, g2, acc0[j]);
+          acc1[j] = ffma2(v0, h2, acc1[j]);
+        } else if (MODE == MODE_MID) {
+          acc0[j] = ffma2(v0, g2, acc0[j]);
+          acc1[j] = ffma2(v0, h2, acc1[j]);
+          acc1[j] = ffma2(v1, g2, acc1[j]);
+        } else {
+          acc0[j] = ffma2(v0, h2, acc0[j]);
+          acc0[j] = ffma2(v1, g2, acc0[j]);
+        }
+      }
+    }
+    scatter_rows<R, MODE, NB, COLS, K + 1>(p0, p1, acc0, acc1, w);
+  }
+}
+
+
 // Tiled variant of the strided sweep (the default when rows are 16-byte aligned).
 // A CTA stages a tall input tile - (NB*NSEGS + 2R) rows x COLS columns of each
 // input - in shared memory with 16-byte cp.async copies (all in flight at once),
-// then every thread runs the same register-blocked scatter over NSEGS segments of
-// NB outputs reading shared memory at compile-time offsets.  Compared with reading
-// global memory directly this cuts the L2->SM traffic from (NB+2R)/NB to
-// (NB*NSEGS+2R)/(NB*NSEGS) times the input and removes the per-load address
-// arithmetic from the FFMA stream.
+// then every thread runs the register-blocked scatter over NB outputs of TWO
+// adjacent columns at once: inputs are 8-byte shared loads at compile-time
+// offsets, the arithmetic is packed FFMA2 with the tap weight as the broadcast
+// scalar operand (a uniform register), i.e. half the FP32 issue slots of the
+// scalar form.  Compared with reading global memory directly the tile cuts the
+// L2->SM traffic from (NB+2R)/NB to (NB*NSEGS+2R)/(NB*NSEGS) times the input.
 // grid = (ceil(inner / COLS), ceil(n_axis / (NB*NSEGS)), outer), block = THREADS.
 template <int R, int MODE, int NB, int NSEGS, int COLS, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 2)
 conv_strided_tile_kernel(const float* __restrict__ in0, const float* __restrict__ in1,
                          float* __restrict__ out0, float* __restrict__ out1, int n_axis,
                          int64_t inner, int64_t outer_stride,
@@ -105,7 +151,9 @@ conv_strided_tile_kernel(const float* __restrict__ in0, const float* __restrict_
   constexpr int NBT = NB * NSEGS;
   constexpr int ROWS = NBT + 2 * R;
   constexpr int CH = COLS / 4;                 // 16-byte chunks per row
-  constexpr int GROUPS = THREADS / COLS;       // threads sharing a column
+  constexpr int PAIRS = COLS / 2;              // column pairs per tile
+  constexpr int GROUPS = THREADS / PAIRS;      // threads sharing a column pair
+  static_assert(THREADS % PAIRS == 0, "THREADS must be a multiple of COLS / 2");
   extern __shared__ __align__(16) float tile[];
   float* t0 = tile;
   float* t1 = tile + ROWS * COLS;
@@ -116,7 +164,7 @@ conv_strided_tile_kernel(const float* __restrict__ in0, const float* __restrict_
     s_off[k] = (int64_t)reflect_index(a0 - R + k, n_axis) * inner;
   __syncthreads();
   const int64_t base = (int64_t)blockIdx.z * outer_stride + c0;
-  const int ncols = (int)((inner - c0) < COLS ? (inner - c0) : COLS);
+  const int ncols = (int)((inner - c0) < COLS ? (inner - c0) : COLS);   // multiple of 4
   for (int i = threadIdx.x; i < ROWS * CH; i += THREADS) {
     const int row = i / CH, ch = i - row * CH;
     if (ch * 4 < ncols) {
@@ -129,37 +177,16 @@ conv_strided_tile_kernel(const float* __restrict__ in0, const float* __restrict_
   __pipeline_wait_prior(0);
   __syncthreads();
 
-  const int col = threadIdx.x % COLS;
+  const int col = (threadIdx.x % PAIRS) * 2;
   if (col >= ncols) return;
-  for (int seg = threadIdx.x / COLS; seg < NSEGS; seg += GROUPS) {
-    float acc0[NB], acc1[NB];
+  for (int seg = threadIdx.x / PAIRS; seg < NSEGS; seg += GROUPS) {
+    if (a0 + seg * NB >= n_axis) break;
+    float2 acc0[NB], acc1[NB];
 #pragma unroll
-    for (int j = 0; j < NB; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+    for (int j = 0; j < NB; ++j) { acc0[j] = make_float2(0.f, 0.f); acc1[j] = make_float2(0.f, 0.f); }
     const float* p0 = t0 + seg * NB * COLS + col;
     const float* p1 = t1 + seg * NB * COLS + col;
-#pragma unroll
-    for (int k = 0; k < NB + 2 * R; ++k) {
-      const float v0 = p0[k * COLS];
-      const float v1 = (MODE == MODE_FIRST) ? 0.f : p1[k * COLS];
-#pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        const int t = k - j;
-        if (t >= 0 && t <= 2 * R) {
-          const int wi = t >= R ? t - R : R - t;
-          if (MODE == MODE_FIRST) {
-            acc0[j] = fmaf(w.g[wi], v0, acc0[j]);
-            acc1[j] = fmaf(w.h[wi], v0, acc1[j]);
-          } else if (MODE == MODE_MID) {
-            acc0[j] = fmaf(w.g[wi], v0, acc0[j]);
-            acc1[j] = fmaf(w.h[wi], v0, acc1[j]);
-            acc1[j] = fmaf(w.g[wi], v1, acc1[j]);
-          } else {
-            acc0[j] = fmaf(w.h[wi], v0, acc0[j]);
-            acc0[j] = fmaf(w.g[wi], v1, acc0[j]);
-          }
-        }
-      }
-    }
+    scatter_rows<R, MODE, NB, COLS, 0>(p0, p1, acc0, acc1, w);
     const int64_t ob = base + col;
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
@@ -167,10 +194,10 @@ conv_strided_tile_kernel(const float* __restrict__ in0, const float* __restrict_
       if (a < n_axis) {
         const int64_t o = ob + (int64_t)a * inner;
         if (MODE == MODE_LAST) {
-          out0[o] = acc0[j] * scale;
+          *reinterpret_cast<float2*>(out0 + o) = make_float2(acc0[j].x * scale, acc0[j].y * scale);
         } else {
-          out0[o] = acc0[j];
-          out1[o] = acc1[j];
+          *reinterpret_cast<float2*>(out0 + o) = acc0[j];
+          *reinterpret_cast<float2*>(out1 + o) = acc1[j];
         }
       }
     }

@@ -151,19 +151,20 @@ conv_x_tma_kernel(const __grid_constant__ CUtensorMap tm_in,
       // in the operand-reuse cache across the FFMAs and each FFMA reads a single
       // register (its accumulator) from the banks - no bank conflicts, and 32
       // independent accumulation chains per thread
-      float accA[16], accB[16];
+      // (A, B) of one output share an FFMA2: the pair (g, h) is a 64-bit uniform
+      // operand, the input value the broadcast scalar
+      float2 acc[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) { accA[j] = 0.f; accB[j] = 0.f; }
+      for (int j = 0; j < 16; ++j) acc[j] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int i = G::R4 - R; i < G::R4 + 16 + R; ++i) {
-        const float v = win[i];
+        const float2 vv = make_float2(win[i], win[i]);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int t = i - (G::R4 + j);
           if (t >= -R && t <= R) {
             const int wi = t < 0 ? -t : t;
-            accA[j] = fmaf(w.g[wi], v, accA[j]);
-            accB[j] = fmaf(w.h[wi], v, accB[j]);
+            acc[j] = ffma2(vv, w.gh[wi], acc[j]);
           }
         }
       }
@@ -174,9 +175,9 @@ conv_x_tma_kernel(const __grid_constant__ CUtensorMap tm_in,
         const int co = seg * 4 + q;
         const int off = (co >> 3) * kBoxBytes + (((co & 7) << 4) ^ key);
         *reinterpret_cast<float4*>(oa + off) =
-            make_float4(accA[4 * q], accA[4 * q + 1], accA[4 * q + 2], accA[4 * q + 3]);
+            make_float4(acc[4 * q].x, acc[4 * q + 1].x, acc[4 * q + 2].x, acc[4 * q + 3].x);
         *reinterpret_cast<float4*>(ob + off) =
-            make_float4(accB[4 * q], accB[4 * q + 1], accB[4 * q + 2], accB[4 * q + 3]);
+            make_float4(acc[4 * q].y, acc[4 * q + 1].y, acc[4 * q + 2].y, acc[4 * q + 3].y);
       }
     }
     fence_proxy_async();

@@ -57,7 +57,8 @@ constexpr int kTile = 256;
 __global__ void __launch_bounds__(kTile)
 prune_edges_kernel(const mmb_cand* __restrict__ cand, const int* __restrict__ n_ptr, int n_max,
                    const __grid_constant__ SigmaLadder ladder, double overlap, int Y, int X,
-                   int2* __restrict__ edges, int edge_cap, int* __restrict__ edge_count) {
+                   int2* __restrict__ edges, int edge_cap, int* __restrict__ edge_count,
+                   int z_sorted) {
   __shared__ mmb_cand tile[kTile];
   __shared__ double sigmas[kMaxSigmas];
   // the candidate count lives on the device (no host round trip); the grid is
@@ -76,12 +77,17 @@ prune_edges_kernel(const mmb_cand* __restrict__ cand, const int* __restrict__ n_
   // spheres can only touch when |d| <= (s1+s2)*sqrt(3) <= 2*smax*sqrt(3)
   const float cut = (float)(2.0 * smax * 1.7320508075688772) + 1.0f;
   const float cut2 = cut * cut;
+  // candidates listed by ascending z (the global prune of the seamless mode): once
+  // a tile starts farther above this block's last candidate than the cut-off, so
+  // does every later tile
+  const int z_block_max = z_sorted ? cand[min(n, (int)(blockIdx.x + 1) * kTile) - 1].z : 0;
   // tiles with j > i only: start at this block's own tile
   for (int j0 = blockIdx.x * kTile; j0 < n; j0 += kTile) {
     __syncthreads();
     const int jl = j0 + threadIdx.x;
     if (jl < n) tile[threadIdx.x] = cand[jl];
     __syncthreads();
+    if (z_sorted && (float)(tile[0].z - z_block_max) > cut) break;      // block-uniform
     if (i >= n) continue;
     const int cnt = n - j0 < kTile ? n - j0 : kTile;
     for (int t = 0; t < cnt; ++t) {
@@ -163,20 +169,33 @@ int make_ladder(const double* sigmas_host, int num_sigma, SigmaLadder* out) {
   return MMB_OK;
 }
 
+__global__ void keep_all_kernel(const int* __restrict__ n_ptr, int n_max, uint8_t* __restrict__ keep) {
+  const int n = min(*n_ptr, n_max);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keep[i] = 1;
+}
+
 // Fully asynchronous pruning of the first min(*n_ptr, n_max) candidates.  Scratch is
 // caller-provided: edges[edge_cap], edge_count (1 int), state[2 * (n_max + 8)] bytes.
 // *edge_count may exceed edge_cap afterwards: the caller must check and redo.
 int prune_within_enqueue(const mmb_cand* cand, const int* n_ptr, int n_max,
                          const SigmaLadder& ladder, double overlap, int Y, int X, int2* edges,
                          int edge_cap, int* edge_count, unsigned char* state, uint8_t* keep,
-                         cudaStream_t st) {
+                         cudaStream_t st, int z_sorted) {
   if (n_max <= 0) return MMB_OK;
   const int64_t npad = (n_max + 3) / 4 * 4 + 4;
   MMB_CHECK_CUDA(cudaMemsetAsync(edge_count, 0, sizeof(int), st));
+  if (overlap >= 1.0) {
+    // the overlap fraction never exceeds 1, so nothing can be removed: the callers
+    // that prune later over a larger candidate set (seamless slabs) land here
+    keep_all_kernel<<<(unsigned)cdiv(n_max, 256), 256, 0, st>>>(n_ptr, n_max, keep);
+    MMB_CHECK_LAUNCH();
+    return MMB_OK;
+  }
   {
     ProfScope ps(PROF_PRUNE_EDGES, n_max, st);
     prune_edges_kernel<<<(unsigned)cdiv(n_max, kTile), kTile, 0, st>>>(
-        cand, n_ptr, n_max, ladder, overlap, Y, X, edges, edge_cap, edge_count);
+        cand, n_ptr, n_max, ladder, overlap, Y, X, edges, edge_cap, edge_count, z_sorted);
   }
   MMB_CHECK_LAUNCH();
   {
@@ -189,7 +208,7 @@ int prune_within_enqueue(const mmb_cand* cand, const int* n_ptr, int n_max,
 }
 
 int prune_within_impl(const mmb_cand* cand, int n, const double* sigmas_host, int num_sigma,
-                      double overlap, int Y, int X, uint8_t* keep, cudaStream_t st) {
+                      double overlap, int Y, int X, uint8_t* keep, cudaStream_t st, int z_sorted) {
   if (n == 0) return MMB_OK;
   SigmaLadder ladder;
   int rc = make_ladder(sigmas_host, num_sigma, &ladder);
@@ -206,7 +225,7 @@ int prune_within_impl(const mmb_cand* cand, int n, const double* sigmas_host, in
   for (int attempt = 0; attempt < 2; ++attempt) {
     MMB_CHECK_CUDA(cudaMallocAsync((void**)&d_edges, (size_t)edge_cap * sizeof(int2), st));
     rc = prune_within_enqueue(cand, d_counts, n, ladder, overlap, Y, X, d_edges, edge_cap,
-                              d_counts + 1, d_state, keep, st);
+                              d_counts + 1, d_state, keep, st, z_sorted);
     if (rc) return rc;
     MMB_CHECK_CUDA(cudaMemcpyAsync(&n_edges, d_counts + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
     MMB_CHECK_CUDA(cudaStreamSynchronize(st));
@@ -274,7 +293,16 @@ extern "C" int mmb_prune_within(const mmb_cand* cand, int n, const double* sigma
   MMB_REQUIRE(n >= 0 && num_sigma > 0 && sigmas, "bad arguments");
   MMB_REQUIRE(n == 0 || (cand && keep), "null buffer");
   return mmb::prune_within_impl(cand, n, sigmas, num_sigma, overlap, Y, X, keep,
-                                (cudaStream_t)stream);
+                                (cudaStream_t)stream, 0);
+}
+
+extern "C" int mmb_prune_within_zsorted(const mmb_cand* cand, int n, const double* sigmas,
+                                        int num_sigma, double overlap, int Y, int X,
+                                        uint8_t* keep, void* stream) {
+  MMB_REQUIRE(n >= 0 && num_sigma > 0 && sigmas, "bad arguments");
+  MMB_REQUIRE(n == 0 || (cand && keep), "null buffer");
+  return mmb::prune_within_impl(cand, n, sigmas, num_sigma, overlap, Y, X, keep,
+                                (cudaStream_t)stream, 1);
 }
 
 extern "C" int mmb_prune_seams(const int32_t* master_zyx, int n_master, const int32_t* check_zyx,

@@ -179,12 +179,16 @@ class StackDetector(object):
 
     @classmethod
     def detect_blobs_sub_rois(cls, img5d, img, sub_roi_slices, sub_rois_offsets,
-                              denoise_max_shape, exclude_border, coloc, channel):
+                              denoise_max_shape, exclude_border, coloc, channel, coords=None):
         """Run every sub-ROI through the GPU in z, y, x order and collect the
         blob tables in an object array shaped like the chunk grid
         (stack_detect.py:175-257).  The reference fans out over a process pool;
         here sub-ROIs are enqueued back to back on one stream and their tables
-        are assembled on the host while later sub-ROIs compute."""
+        are assembled on the host while later sub-ROIs compute.
+
+        ``coords`` (not in the reference) restricts the work to a subset of the
+        chunk grid; the other cells stay None.  ``multi_gpu`` uses it to give
+        every rank its share of the chunks."""
         from collections import deque
         from .. import gpu
         last_coord = np.subtract(sub_roi_slices.shape, 1)
@@ -208,7 +212,8 @@ class StackDetector(object):
             coord, segments = cls.finish_sub_roi(pending.popleft())
             seg_rois[coord] = segments
 
-        for coord in np.ndindex(*sub_roi_slices.shape):
+        todo = np.ndindex(*sub_roi_slices.shape) if coords is None else [tuple(c) for c in coords]
+        for coord in todo:
             while pending and cls._workspace(tuple(largest)).free_slots() < n_chl:
                 finish_oldest()
             pending.append(cls.enqueue_sub_roi(
@@ -218,7 +223,9 @@ class StackDetector(object):
             finish_oldest()
         # a table with zero rows is stored as None, like the reference
         for coord in np.ndindex(*seg_rois.shape):
-            if seg_rois[coord] is not None and len(seg_rois[coord]) == 0:
+            if isinstance(seg_rois[coord], int):       # cells never filled keep the zeros() default
+                seg_rois[coord] = None
+            elif seg_rois[coord] is not None and len(seg_rois[coord]) == 0:
                 seg_rois[coord] = None
         return seg_rois
 

@@ -185,12 +185,15 @@ def localmax(prev, cur, nxt, X: int, s: int, thr: float, cand: torch.Tensor,
 
 
 def prune_within(cand: torch.Tensor, n: int, sigmas: Sequence[float], overlap: float, Y: int,
-                 X: int) -> torch.Tensor:
+                 X: int, z_sorted: bool = False) -> torch.Tensor:
+    """keep flags of ``_prune_blobs``; ``z_sorted`` promises candidates listed by
+    ascending z (``mmb_prune_within_zsorted``: same result, windowed pair search)."""
     lib = _lib.load()
     keep = torch.zeros(max(n, 1), dtype=torch.uint8, device=cand.device)
     sig = (C.c_double * len(sigmas))(*[float(s) for s in sigmas])
-    _lib.check(lib.mmb_prune_within(_ptr(cand), int(n), sig, len(sigmas), float(overlap), int(Y),
-                                    int(X), _ptr(keep), _stream()))
+    fn = lib.mmb_prune_within_zsorted if z_sorted else lib.mmb_prune_within
+    _lib.check(fn(_ptr(cand), int(n), sig, len(sigmas), float(overlap), int(Y), int(X),
+                  _ptr(keep), _stream()))
     return keep[:n]
 
 

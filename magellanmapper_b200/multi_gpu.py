@@ -1,0 +1,403 @@
+"""Blob detection over several GPUs of one box: one process per GPU,
+``torch.distributed`` (NCCL over NVLink on the GPUs, gloo in the CPU tests).
+
+The reference spreads sub-ROIs over a ``multiprocessing.Pool``
+(``magmap/cv/stack_detect.py:175-257``, ``chunking.py:143-167``); here the same
+sub-ROIs are spread over GPUs.  Two shardings:
+
+* **chunk-faithful z-slabs** (``detect_blobs_blocks_slabs``): the volume lives
+  as contiguous z-slabs, one per rank.  The reference's chunk grid
+  (``chunking.stack_splitter``) is laid over the WHOLE volume; chunk z-rows are
+  dealt to the rank holding their first plane, the planes a chunk row needs
+  from other slabs (its 5-voxel overlap, and whatever the 500-voxel chunk
+  pitch leaves on the far side of a slab face) arrive by ``send/recv`` between
+  slab neighbours, chunks run independently, the per-chunk tables are gathered
+  to rank 0 (sizes, then payload) and ``StackPruner.prune_blobs_mp`` removes
+  the seam duplicates there.  Row for row equal to the single-GPU result.
+* **seamless z-slabs** (``detect_seamless``): the volume is one chunk.  Each
+  rank filters its slab extended by a halo of ``halo_planes`` (>= r_max + 1
+  planes of real neighbour data, rounded to whole preprocessing block layers),
+  keeps the local maxima of the planes it owns, the candidates are gathered to
+  rank 0 and ``_prune_blobs`` runs once over all of them.  Equal to one chunk
+  covering the whole volume.
+
+Nothing here touches voxel arithmetic: that is the CUDA library's.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+Range = Tuple[int, int]
+
+
+# ----------------------------------------------------------------------------
+# geometry (pure integer host logic; covered by the CPU tests)
+# ----------------------------------------------------------------------------
+
+def slab_bounds(n_planes: int, world: int, align: int = 1) -> List[Range]:
+    """Contiguous z-slabs [z0, z1), one per rank, faces on multiples of
+    ``align`` (the preprocessing block depth in seamless mode); trailing ranks
+    may be empty when there are fewer aligned layers than ranks."""
+    n_layers = -(-int(n_planes) // int(align))
+    cuts = [min(int(n_planes), (n_layers * r // world) * align) for r in range(world)]
+    cuts.append(int(n_planes))
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def owner_of(z: int, held: Sequence[Range]) -> int:
+    for r, (a, b) in enumerate(held):
+        if a <= z < b:
+            return r
+    raise ValueError(f"plane {z} is held by no rank: {held}")
+
+
+def assign_chunk_rows(z_starts: Sequence[int], held: Sequence[Range]) -> List[List[int]]:
+    """Chunk z-row ``k`` (first plane ``z_starts[k]``) goes to the rank whose
+    slab holds that plane, so a rank fetches planes only from slabs after its
+    own."""
+    rows: List[List[int]] = [[] for _ in held]
+    for k, z in enumerate(z_starts):
+        rows[owner_of(int(z), held)].append(k)
+    return rows
+
+
+def wanted_range(rows: Sequence[int], z_bounds: Sequence[Range], held: Range) -> Range:
+    """Planes a rank must see: its own slab plus every plane of its chunk rows."""
+    lo, hi = held
+    for k in rows:
+        lo, hi = min(lo, z_bounds[k][0]), max(hi, z_bounds[k][1])
+    return lo, hi
+
+
+def transfer_plan(held: Sequence[Range], wanted: Sequence[Range]) -> List[Tuple[int, int, int, int]]:
+    """Every (src, dst, z0, z1) with src != dst: planes [z0, z1) held by ``src``
+    that ``dst`` wants.  Deterministic order, identical on every rank."""
+    plan = []
+    for dst, (w0, w1) in enumerate(wanted):
+        for src, (h0, h1) in enumerate(held):
+            if src == dst:
+                continue
+            z0, z1 = max(w0, h0), min(w1, h1)
+            if z0 < z1:
+                plan.append((src, dst, z0, z1))
+    return plan
+
+
+# ----------------------------------------------------------------------------
+# collectives
+# ----------------------------------------------------------------------------
+
+def _world(group=None) -> Tuple[int, int]:
+    if not dist.is_available() or not dist.is_initialized():
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def _comm_device(group=None) -> torch.device:
+    """NCCL moves device memory, gloo host memory."""
+    if dist.is_initialized() and dist.get_backend(group) == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def exchange_planes(local: torch.Tensor, held: Sequence[Range], wanted: Sequence[Range],
+                    group=None) -> torch.Tensor:
+    """Halo exchange.  ``local`` holds planes ``held[rank]`` of the volume
+    (dim 0 = z); returns a tensor holding ``wanted[rank]`` (a superset), the
+    missing planes received from the ranks that hold them with grouped
+    ``isend/irecv`` (NCCL send/recv over NVLink on the GPUs)."""
+    rank, world = _world(group)
+    h0, h1 = held[rank]
+    w0, w1 = wanted[rank]
+    if local.shape[0] != h1 - h0:
+        raise ValueError(f"rank {rank} holds {local.shape[0]} planes, expected {h1 - h0}")
+    if (w0, w1) == (h0, h1):
+        ext = local
+    else:
+        ext = torch.empty((w1 - w0,) + tuple(local.shape[1:]), dtype=local.dtype,
+                          device=local.device)
+        ext[h0 - w0:h1 - w0].copy_(local)
+    if world == 1:
+        return ext
+    ops, keep = [], []
+    for src, dst, z0, z1 in transfer_plan(held, wanted):
+        if src == rank:
+            buf = local[z0 - h0:z1 - h0].contiguous()
+            keep.append(buf)
+            ops.append(dist.P2POp(dist.isend, buf, dist.get_global_rank(group, dst)
+                                  if group is not None else dst, group))
+        elif dst == rank:
+            view = ext[z0 - w0:z1 - w0]            # contiguous: whole planes
+            ops.append(dist.P2POp(dist.irecv, view, dist.get_global_rank(group, src)
+                                  if group is not None else src, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return ext
+
+
+def gather_rows(rows: Optional[np.ndarray], n_cols: int, group=None, dst: int = 0,
+                dtype=np.float64) -> Optional[List[np.ndarray]]:
+    """Variable-length gather of ``(n_r, n_cols)`` tables to ``dst``: row counts
+    first (``all_gather``), then each payload with ``send/recv``.  Returns the
+    list of per-rank tables on ``dst`` and None elsewhere."""
+    rank, world = _world(group)
+    mine = np.zeros((0, n_cols), dtype=dtype) if rows is None else np.ascontiguousarray(
+        rows, dtype=dtype).reshape(-1, n_cols)
+    if world == 1:
+        return [mine]
+    dev = _comm_device(group)
+    tdtype = torch.from_numpy(np.zeros(1, dtype=dtype)).dtype
+    count = torch.tensor([mine.shape[0]], dtype=torch.int64, device=dev)
+    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(counts, count, group=group)
+    counts = [int(c.item()) for c in counts]
+    g = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+    if rank == dst:
+        out = []
+        for r in range(world):
+            if r == rank:
+                out.append(mine)
+            elif counts[r] == 0:
+                out.append(np.zeros((0, n_cols), dtype=dtype))
+            else:
+                buf = torch.empty((counts[r], n_cols), dtype=tdtype, device=dev)
+                dist.recv(buf, src=g(r), group=group)
+                out.append(buf.cpu().numpy())
+        return out
+    if mine.shape[0]:
+        dist.send(torch.from_numpy(mine).to(dev), dst=g(dst), group=group)
+    return None
+
+
+def pack_tables(seg_rois: np.ndarray) -> Optional[np.ndarray]:
+    """Flatten a chunk-grid object array of blob tables into one table with the
+    chunk coordinate in three trailing columns (``chunking.merge_blobs``)."""
+    from .cv import chunking
+    return chunking.merge_blobs(seg_rois)
+
+
+def unpack_tables(merged_parts: Sequence[np.ndarray], grid_shape: Sequence[int]) -> np.ndarray:
+    """Inverse of ``pack_tables`` over the tables of every rank."""
+    seg_rois = np.empty(tuple(grid_shape), dtype=object)
+    for part in merged_parts:
+        if part is None or len(part) == 0:
+            continue
+        tags = part[:, -3:].astype(np.int64)
+        # rows of one chunk are contiguous in a packed table
+        change = np.flatnonzero(np.any(np.diff(tags, axis=0) != 0, axis=1)) + 1
+        for a, b in zip(np.concatenate(([0], change)), np.concatenate((change, [len(part)]))):
+            seg_rois[tuple(tags[a])] = part[a:b, :-3]
+    return seg_rois
+
+
+# ----------------------------------------------------------------------------
+# chunk-faithful z-slabs
+# ----------------------------------------------------------------------------
+
+def chunk_row_plan(global_shape: Sequence[int], blocks, held: Sequence[Range]):
+    """(rows per rank, z extent of every chunk row, wanted plane range per rank)."""
+    grid = blocks.sub_roi_slices.shape
+    z_bounds = [(blocks.sub_roi_slices[k, 0, 0][0].start, blocks.sub_roi_slices[k, 0, 0][0].stop)
+                for k in range(grid[0])]
+    rows = assign_chunk_rows([b[0] for b in z_bounds], held)
+    wanted = [wanted_range(rows[r], z_bounds, held[r]) for r in range(len(held))]
+    return rows, z_bounds, wanted
+
+
+def detect_blobs_blocks_slabs(filename_base: str, slab, held: Sequence[Range],
+                              global_shape: Sequence[int],
+                              channels: Optional[Sequence[int]] = None, group=None,
+                              save_dfs: bool = False):
+    """``stack_detect.detect_blobs_blocks`` over a volume sharded as z-slabs.
+
+    Args:
+        slab: this rank's planes ``held[rank]`` of the (z, y, x[, c]) volume,
+            a CUDA tensor (uint16 as int16 bits is accepted like everywhere).
+        held: the slab [z0, z1) of every rank, in rank order.
+        global_shape: (Z, Y, X) of the whole volume.
+
+    Returns ``(stats, fdbk, Blobs)`` on rank 0 (identical to the single-GPU
+    call on the whole volume) and ``(None, None, None)`` on the other ranks.
+    """
+    from .cv import detector, stack_detect
+    from .plot import plot_3d
+    from .settings import config
+    from .io import libmag, np_io
+    rank, world = _world(group)
+    if channels is None:
+        _, channels = plot_3d.setup_channels(slab, channels, 3)
+    settings = config.get_roi_profile(channels[0])
+    shape = tuple(int(v) for v in global_shape[:3]) + tuple(slab.shape[3:])
+    blocks = stack_detect.setup_blocks(settings, shape)
+    rows, z_bounds, wanted = chunk_row_plan(shape, blocks, held)
+    ext = exchange_planes(slab, held, wanted, group)
+    w0 = wanted[rank][0]
+
+    grid = blocks.sub_roi_slices.shape
+    local_slices = np.empty(grid, dtype=object)
+    coords = []
+    for k in rows[rank]:
+        for j in range(grid[1]):
+            for i in range(grid[2]):
+                sz, sy, sx = blocks.sub_roi_slices[k, j, i]
+                local_slices[k, j, i] = (slice(sz.start - w0, sz.stop - w0), sy, sx)
+                coords.append((k, j, i))
+    # cells of other ranks still need a shape for the workspace sizing
+    for c in np.ndindex(*grid):
+        if local_slices[c] is None:
+            local_slices[c] = (slice(0, 0), slice(0, 0), slice(0, 0))
+    seg_rois = None
+    if coords:
+        seg_rois = stack_detect.StackDetector.detect_blobs_sub_rois(
+            None, ext, local_slices, blocks.sub_rois_offsets, blocks.denoise_max_shape,
+            blocks.exclude_border, False, channels, coords=coords)
+    packed = pack_tables(seg_rois) if seg_rois is not None else None
+    n_cols = len(detector.Blobs.Cols) + 3 if hasattr(detector.Blobs, "Cols") else 14
+    if packed is not None:
+        n_cols = packed.shape[1]
+    n_cols = _agree_max(n_cols, group)
+    parts = gather_rows(packed, n_cols, group)
+    if rank != 0:
+        return None, None, None
+
+    seg_all = unpack_tables(parts, grid)
+    segments_all, df_pruning = stack_detect.StackPruner.prune_blobs_mp(
+        None, seg_all, blocks.overlap, blocks.tol, blocks.sub_roi_slices,
+        blocks.sub_rois_offsets, channels, blocks.overlap_padding)
+    filename_blobs = libmag.combine_paths(filename_base, config.SUFFIX_BLOBS)
+    blobs = detector.Blobs(segments_all, path=filename_blobs)
+    if segments_all is not None:
+        blobs.replace_rel_with_abs_blob_coords(segments_all)
+        blobs.blobs = segments_all
+        segments_all = blobs.remove_abs_blob_coords(True)
+    blobs.blobs = segments_all
+    blobs.colocalizations = None
+    blobs.resolutions = config.resolutions
+    blobs.roi_offset = (0, 0, 0)
+    blobs.roi_size = shape[:3]
+    if save_dfs and df_pruning is not None and len(df_pruning.columns):
+        df_pruning.to_csv("blob_ratios.csv", index=False)
+    return None, None, blobs
+
+
+def _agree_max(v: int, group=None) -> int:
+    rank, world = _world(group)
+    if world == 1:
+        return int(v)
+    t = torch.tensor([int(v)], dtype=torch.int64, device=_comm_device(group))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return int(t.item())
+
+
+# ----------------------------------------------------------------------------
+# seamless z-slabs
+# ----------------------------------------------------------------------------
+
+def seamless_plan(n_planes: int, world: int, block_depth: int, halo_planes: int):
+    """Owned slabs with faces on multiples of ``block_depth`` and the extended
+    range each rank filters: the halo is rounded up to whole block layers so the
+    25^3 preprocessing blocks of every rank coincide with those of one chunk
+    anchored at the volume origin."""
+    own = slab_bounds(n_planes, world, block_depth)
+    layers = -(-int(halo_planes) // int(block_depth)) * int(block_depth)
+    ext = [(max(0, a - layers), min(int(n_planes), b + layers)) if b > a else (a, b)
+           for a, b in own]
+    return own, ext
+
+
+def detect_seamless(slab, held: Sequence[Range], global_shape: Sequence[int],
+                    channel: int = 0, group=None, tile_yx: Optional[Sequence[int]] = None):
+    """Detect blobs as if the whole volume were ONE chunk (no chunk seams).
+
+    Each rank: exchange halo planes, run the fused chunk driver on its extended
+    slab without pruning and keep the local maxima of the planes it owns
+    (``z_lo``/``z_hi`` of ``mmb_detect_chunk_enqueue``); rank 0: gather the
+    candidates and run ``_prune_blobs`` once over all of them
+    (``mmb_prune_within``).  ``tile_yx`` additionally tiles y and x inside a rank
+    (tile + halo must fit the workspace of eight float volumes).
+
+    Returns on rank 0 the ``(n, 11)`` blob table of ``detector.detect_blobs`` in
+    ``peak_local_max`` order, None elsewhere.
+    """
+    from . import gpu
+    from .cv import detector, stack_detect
+    from .plot import plot_3d
+    from .settings import config
+    rank, world = _world(group)
+    settings = config.get_roi_profile(channel)
+    Z, Y, X = (int(v) for v in global_shape[:3])
+    blocks = stack_detect.setup_blocks(settings, (Z, Y, X))
+    scale = detector.calc_scaling_factor()[2]
+    dms = blocks.denoise_max_shape
+    pre = plot_3d.preproc_params(settings, channel) if dms is not None else None
+    sigmas = detector.sigma_ladder(settings, scale, False)
+    r_max = int(4.0 * float(np.max(sigmas)) + 0.5)
+    halo = r_max + 1
+    bd = (int(dms[0]), int(dms[1]), int(dms[2])) if dms is not None else (1, 1, 1)
+    own, ext_ranges = seamless_plan(Z, world, bd[0], halo)
+    # the caller's slabs need not coincide with the aligned owned slabs
+    ext = exchange_planes(slab, held, ext_ranges, group) if world > 1 or tuple(
+        held[rank]) != tuple(ext_ranges[rank]) else slab
+    e0, e1 = ext_ranges[rank]
+    z0, z1 = own[rank]
+    in_scale = 1.0
+    cands = []
+    if z1 > z0:
+        src_full = gpu.as_source(ext, channel if ext.dim() == 4 else None)
+        if pre is None:
+            in_scale = {gpu._lib.MMB_U8: 1 / 255.0, gpu._lib.MMB_U16: 1 / 65535.0}.get(
+                src_full.dtype, 1.0)
+        ty, tx = (Y, X) if tile_yx is None else (int(tile_yx[0]), int(tile_yx[1]))
+        ty = -(-ty // bd[1]) * bd[1]
+        tx = -(-tx // bd[2]) * bd[2]
+        hy = -(-halo // bd[1]) * bd[1]
+        hx = -(-halo // bd[2]) * bd[2]
+        det = None
+        for y0 in range(0, Y, ty):
+            for x0 in range(0, X, tx):
+                ya, yb = max(0, y0 - hy), min(Y, y0 + ty + hy)
+                xa, xb = max(0, x0 - hx), min(X, x0 + tx + hx)
+                view = ext[:, ya:yb, xa:xb] if ext.dim() == 3 else ext[:, ya:yb, xa:xb, :]
+                src = gpu.as_source(view, channel if ext.dim() == 4 else None)
+                if det is None:
+                    det = gpu.ChunkDetector((e1 - e0, min(Y, ty + 2 * hy), min(X, tx + 2 * hx)))
+                got, _ = det.detect(src, sigmas, settings["detection_threshold"], 1.0,
+                                    scale=in_scale, pre=pre, block_shape=bd,
+                                    z_lo=z0 - e0, z_hi=z1 - e0)
+                if len(got):
+                    yy, xx = got["y"] + ya, got["x"] + xa
+                    keep = (yy >= y0) & (yy < min(Y, y0 + ty)) & (xx >= x0) & (xx < min(X, x0 + tx))
+                    got = got[keep].copy()
+                    got["z"] += e0
+                    got["y"] += ya
+                    got["x"] += xa
+                    cands.append(got)
+    mine = np.concatenate(cands) if cands else np.zeros(0, dtype=gpu.CAND_DTYPE)
+    raw = mine.view(np.int32).reshape(-1, 5)
+    parts = gather_rows(raw, 5, group, dtype=np.int32)
+    if rank != 0:
+        return None
+    allc = np.concatenate(parts).astype(np.int32).reshape(-1).view(gpu.CAND_DTYPE)
+    return prune_global(allc, sigmas, settings["overlap"], (Z, Y, X), channel)
+
+
+def prune_global(cands: np.ndarray, sigmas, overlap: float, shape: Sequence[int], channel: int):
+    """``_prune_blobs`` over the candidates of the whole volume, then the blob
+    table of ``detector.detect_blobs`` in ``peak_local_max`` order."""
+    from . import gpu
+    from .cv import detector
+    if len(cands) == 0:
+        return None
+    Z, Y, X = (int(v) for v in shape)
+    # z-sorted input lets the pair kernel skip tiles farther than the cut-off
+    order = np.argsort(cands["z"], kind="stable")
+    cands = cands[order]
+    dev = gpu.cands_from_numpy(cands)
+    keep = gpu.prune_within(dev, len(cands), sigmas, overlap, Y, X, z_sorted=True)
+    keep = keep.cpu().numpy().astype(bool)
+    return detector.cands_to_blobs(cands[keep], sigmas, (Y, X), channel)
