@@ -7,7 +7,7 @@ One step = one pass of ``detect_blobs_blocks`` (chunked preprocessing, 10-scale
 LoG, 4-D local maxima, overlap pruning, seam pruning) over one synthetic
 cleared-tissue stack.  N=1 runs BASELINE config 2, 512x2048x2048 uint16 with
 the ``roi_blobs`` profile at 1 um isotropic resolution (50 chunks).  N>1 runs
-one such stack per GPU as z-slabs of a N*512-plane volume (see ``--mode``).
+one such stack per GPU as the z-slabs of ONE N*512-plane volume (multi_gpu.detect_blobs_blocks_slabs).
 
 Prints ONE JSON line (rank 0).  ``value`` = GVoxel/s with the stack resident in
 HBM; ``e2e`` = the same through the public API from pinned HOST memory,
@@ -243,9 +243,22 @@ def main():
     img5d_dev = np_io.Image5d(vol[None])
     nvox = float(np.prod(shape))
 
+    # N > 1: the ranks' stacks are the z-slabs of ONE world*Z-plane volume.  The
+    # reference's chunk grid is laid over the whole volume, chunk rows are dealt to
+    # the slab holding their first plane, missing planes arrive by NCCL send/recv
+    # (halo exchange), tables are gathered to rank 0 and seam-pruned there.
+    from magellanmapper_b200 import multi_gpu
+    held = multi_gpu.slab_bounds(shape[0] * world, world)
+    gshape = (shape[0] * world, shape[1], shape[2])
+
     def step_resident():
-        _, _, blobs = stack_detect.detect_blobs_blocks(
-            os.path.join(tmp, f"bench_r{rank}"), img5d_dev, None, None, [0], False, False, True)
+        if world == 1:
+            _, _, blobs = stack_detect.detect_blobs_blocks(
+                os.path.join(tmp, f"bench_r{rank}"), img5d_dev, None, None, [0], False, False,
+                True)
+        else:
+            _, _, blobs = multi_gpu.detect_blobs_blocks_slabs(
+                os.path.join(tmp, f"bench_r{rank}"), vol, held, gshape, [0])
         return blobs
 
     def barrier():
@@ -254,6 +267,7 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    lib.mmb_profile_enable(1)          # warm the library's event pool as well
     for _ in range(args.warmup):
         step_resident()
 
@@ -273,7 +287,9 @@ def main():
     wall = time.perf_counter() - t0
     dev_ms = ev0.elapsed_time(ev1)
     launches = lib.mmb_launch_count() - launches0
-    n_blobs = 0 if blobs.blobs is None else len(blobs.blobs)
+    n_blobs = 0 if blobs is None or blobs.blobs is None else len(blobs.blobs)
+    stage_times = None if blobs is None or not getattr(blobs, "times", None) else {
+        k.value: round(float(v[0]), 4) for k, v in blobs.times.items()}
     import ctypes as C
     ms = (C.c_double * 10)(); cnt = (C.c_int64 * 10)(); units = (C.c_double * 10)()
     lib.mmb_profile_collect(ms, cnt, units)
@@ -300,8 +316,15 @@ def main():
         img5d_host.is_roi = True
 
         def step_e2e():
-            _, _, b = stack_detect.detect_blobs_stack(os.path.join(tmp, f"e2e_r{rank}"),
-                                                      img5d_host)
+            if world == 1:
+                _, _, b = stack_detect.detect_blobs_stack(os.path.join(tmp, f"e2e_r{rank}"),
+                                                          img5d_host)
+            else:
+                slab = host.to(device, non_blocking=True)
+                _, _, b = multi_gpu.detect_blobs_blocks_slabs(
+                    os.path.join(tmp, f"e2e_r{rank}"), slab, held, gshape, [0])
+                if b is not None:
+                    b.save_archive()
             return b
 
         b = step_e2e()                                    # warm the pinned path once
@@ -315,9 +338,14 @@ def main():
             tt = torch.tensor([t_e2e], device=device, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             t_e2e = float(tt.item())
-        d2h = 0 if b.blobs is None else int(b.blobs.shape[0]) * 20
+        nb_e2e = 0 if b is None or b.blobs is None else int(b.blobs.shape[0])
+        if world > 1:
+            tt = torch.tensor([nb_e2e], device=device, dtype=torch.int64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            nb_e2e = int(tt.item())
+        d2h = nb_e2e * 20
         e2e = {"value": nvox * world * args.steps / t_e2e / 1e9, "unit": UNIT,
-               "h2d_bytes_per_step": int(nvox * 2), "d2h_bytes_per_step": d2h}
+               "h2d_bytes_per_step": int(nvox * 2) * world, "d2h_bytes_per_step": d2h}
         del host, host_np, img5d_host
 
     if rank != 0:
@@ -370,7 +398,11 @@ def main():
                                f"LoG sigma 3..5, 4-D local maxima, overlap + seam pruning), "
                                f"chunk-faithful, 500^3-voxel chunks with 5-voxel overlap",
                    "l2": "inputs larger than L2 (every sweep streams >= 1 GB per launch)",
-                   "blobs_per_step": n_blobs},
+                   "blobs_per_step": n_blobs, "host_stage_s_last_step": stage_times,
+                   "multi_gpu": None if world == 1 else
+                   f"{world} z-slabs of one {gshape[0]}x{gshape[1]}x{gshape[2]} volume, chunk rows "
+                   f"dealt to the slab of their first plane, halo planes by NCCL send/recv, "
+                   f"tables gathered to rank 0 and seam-pruned there"},
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
         "clocks": clocks,
     }

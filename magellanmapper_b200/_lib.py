@@ -12,7 +12,7 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmmb200.so")
+LIB_PATH = os.environ.get("MMB200_LIB") or os.path.join(_HERE, "libmmb200.so")   # env override: developer A/B builds
 
 MMB_U8, MMB_U16, MMB_F32, MMB_F64 = 0, 1, 2, 3
 MMB_OK, MMB_ERR_INVALID, MMB_ERR_CUDA, MMB_ERR_OVERFLOW, MMB_ERR_UNSUPPORTED = 0, -1, -2, -3, -4

@@ -72,10 +72,27 @@ static std::vector<ProfRec> g_prof;
 static std::atomic<bool> g_prof_on{false};
 static thread_local ProfRec t_open;
 
+// events are recycled: creating two per launch would put thousands of
+// cudaEventCreate calls inside a timed step
+static std::vector<cudaEvent_t> g_event_pool;
+static cudaEvent_t take_event() {
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_event_pool.empty()) {
+      cudaEvent_t e = g_event_pool.back();
+      g_event_pool.pop_back();
+      return e;
+    }
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
 bool prof_enabled() { return g_prof_on.load(std::memory_order_relaxed); }
 void prof_begin(int kind, double units, cudaStream_t st) {
   t_open.kind = kind; t_open.units = units;
-  cudaEventCreate(&t_open.a); cudaEventCreate(&t_open.b);
+  t_open.a = take_event(); t_open.b = take_event();
   cudaEventRecord(t_open.a, st);
 }
 void prof_end(cudaStream_t st) {
@@ -102,6 +119,9 @@ int prune_within_enqueue(const mmb_cand* cand, const int* n_ptr, int n_max,
                          const SigmaLadder& ladder, double overlap, int Y, int X, int2* edges,
                          int edge_cap, int* edge_count, unsigned char* state, uint8_t* keep,
                          cudaStream_t st, int z_sorted);
+
+int sort_by_z_enqueue(const mmb_cand* cand, const int* n_ptr, int n_max, int Z, int* hist,
+                      mmb_cand* out, cudaStream_t st);
 
 // stable stream compaction of the survivors to the front of a second buffer
 __global__ void compact_kernel(const mmb_cand* __restrict__ in, const uint8_t* __restrict__ keep,
@@ -132,7 +152,7 @@ extern "C" int64_t mmb_launch_count(void) { return g_launches.load(); }
 
 extern "C" int mmb_profile_enable(int on) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto& r : g_prof) { g_event_pool.push_back(r.a); g_event_pool.push_back(r.b); }
   g_prof.clear();
   g_prof_on.store(on != 0);
   return MMB_OK;
@@ -147,16 +167,17 @@ extern "C" int mmb_profile_collect(double* ms, int64_t* launches, double* units)
     float t = 0.f;
     MMB_CHECK_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
     ms[r.kind] += t; launches[r.kind] += 1; units[r.kind] += r.units;
-    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    g_event_pool.push_back(r.a); g_event_pool.push_back(r.b);
   }
   g_prof.clear();
   return MMB_OK;
 }
 
 // ---- fused per-chunk driver -------------------------------------------------------
-// work layout: [F][ring0][ring1][ring2][A][B][C][D][cand2][keep][edges][state][counters]
+// work layout:
+// [F][ring0][ring1][ring2][A][B][C][D][cand2][cand3][zhist][keep][edges][state][counters]
 struct ChunkLayout {
-  int64_t vol_b, cand_b, keep_b, edges_b, state_b, total;
+  int64_t vol_b, cand_b, zhist_b, keep_b, edges_b, state_b, total;
   int edge_cap;
 };
 
@@ -164,11 +185,12 @@ static ChunkLayout chunk_layout(int Z, int Y, int64_t pitch, int capacity) {
   ChunkLayout L;
   L.vol_b = align256((int64_t)Z * Y * pitch * (int64_t)sizeof(float));
   L.cand_b = align256((int64_t)capacity * (int64_t)sizeof(mmb_cand));
+  L.zhist_b = align256((int64_t)Z * (int64_t)sizeof(int));
   L.keep_b = align256(capacity);
   L.edge_cap = 4 * capacity + 4096;
   L.edges_b = align256((int64_t)L.edge_cap * (int64_t)sizeof(int2));
   L.state_b = align256(2 * ((int64_t)(capacity + 3) / 4 * 4 + 4));
-  L.total = 8 * L.vol_b + L.cand_b + L.keep_b + L.edges_b + L.state_b + 256;
+  L.total = 8 * L.vol_b + 2 * L.cand_b + L.zhist_b + L.keep_b + L.edges_b + L.state_b + 256;
   return L;
 }
 
@@ -202,6 +224,8 @@ extern "C" int mmb_detect_chunk_enqueue(const void* in, int dtype, const int64_t
   float* lw = (float*)(base + 4 * L.vol_b);       // A,B,C,D (log_scale_impl strides by Z*Y*pitch)
   char* tail = base + 8 * L.vol_b;
   mmb_cand* cand2 = (mmb_cand*)tail;                    tail += L.cand_b;
+  mmb_cand* cand3 = (mmb_cand*)tail;                    tail += L.cand_b;
+  int* zhist = (int*)tail;                              tail += L.zhist_b;
   uint8_t* keep = (uint8_t*)tail;                       tail += L.keep_b;
   int2* edges = (int2*)tail;                            tail += L.edges_b;
   unsigned char* state = (unsigned char*)tail;          tail += L.state_b;
@@ -231,12 +255,19 @@ extern "C" int mmb_detect_chunk_enqueue(const void* in, int dtype, const int64_t
                        capacity, counters, st);
     if (rc) return rc;
   }
-  rc = prune_within_enqueue(cand2, counters, capacity, ladder, overlap, Y, X, edges, L.edge_cap,
-                            counters + 2, state, keep, st, 0);
+  // list the local maxima by plane so that the pair search of the pruning stops at
+  // the cut-off distance in z instead of visiting every pair
+  {
+    ProfScope ps(PROF_COMPACT, capacity, st);
+    rc = sort_by_z_enqueue(cand2, counters, capacity, Z, zhist, cand3, st);
+    if (rc) return rc;
+  }
+  rc = prune_within_enqueue(cand3, counters, capacity, ladder, overlap, Y, X, edges, L.edge_cap,
+                            counters + 2, state, keep, st, 1);
   if (rc) return rc;
   {
     ProfScope ps(PROF_COMPACT, capacity, st);
-    compact_kernel<<<(unsigned)cdiv(capacity, 256), 256, 0, st>>>(cand2, keep, counters, capacity,
+    compact_kernel<<<(unsigned)cdiv(capacity, 256), 256, 0, st>>>(cand3, keep, counters, capacity,
                                                                   cand, counters + 1);
   }
   MMB_CHECK_LAUNCH();

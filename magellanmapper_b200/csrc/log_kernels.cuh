@@ -21,6 +21,14 @@ namespace mmb {
 
 enum { MODE_FIRST = 0, MODE_MID = 1, MODE_LAST = 2 };
 
+// marching sweep shape: NB outputs per thread, G row groups per CTA (STEP = NB * G)
+#ifndef MMB_MARCH_NB
+#define MMB_MARCH_NB 8
+#endif
+#ifndef MMB_MARCH_G
+#define MMB_MARCH_G 4
+#endif
+
 // Packed FP32 FMA of sm_100 (SASS FFMA2): two independent IEEE fp32 fmas per lane
 // in one issue slot.  The sweeps are FP32-issue bound, so every inner loop below
 // is written on float2 values; ptxas folds a (w, w) or (v, v) operand into the
@@ -107,23 +115,28 @@ __device__ __forceinline__ void scatter_rows(const float* __restrict__ p0,
     const float2 v0 = *reinterpret_cast<const float2*>(p0 + K * COLS);
     float2 v1 = make_float2(0.f, 0.f);
     if (MODE != MODE_FIRST) v1 = *reinterpret_cast<const float2*>(p1 + K * COLS);
+    // three passes over the NB accumulators so that the two FFMA2s that update the
+    // same accumulator (h*v0 then g*v1) are NB issue slots apart, not back to back
 #pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      const int t = K - j;
-      if (t >= 0 && t <= 2 * R) {
-        const int wi = t >= R ? t - R : R - t;
-        const float2 g2 = make_float2(w.g[wi], w.g[wi]);
-        const float2 h2 = make_float2(w.h[wi], w.h[wi]);
-        if (MODE == MODE_FIRST) {
-          acc0[j] = ffma2(v0, g2, acc0[j]);
-          acc1[j] = ffma2(v0, h2, acc1[j]);
-        } else if (MODE == MODE_MID) {
-          acc0[j] = ffma2(v0, g2, acc0[j]);
-          acc1[j] = ffma2(v0, h2, acc1[j]);
-          acc1[j] = ffma2(v1, g2, acc1[j]);
-        } else {
-          acc0[j] = ffma2(v0, h2, acc0[j]);
-          acc0[j] = ffma2(v1, g2, acc0[j]);
+    for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const int t = K - j;
+        if (t >= 0 && t <= 2 * R) {
+          const int wi = t >= R ? t - R : R - t;
+          const float2 g2 = make_float2(w.g[wi], w.g[wi]);
+          const float2 h2 = make_float2(w.h[wi], w.h[wi]);
+          if (MODE == MODE_FIRST) {
+            if (pass == 0) acc0[j] = ffma2(v0, g2, acc0[j]);
+            if (pass == 1) acc1[j] = ffma2(v0, h2, acc1[j]);
+          } else if (MODE == MODE_MID) {
+            if (pass == 0) acc1[j] = ffma2(v0, h2, acc1[j]);
+            if (pass == 1) acc0[j] = ffma2(v0, g2, acc0[j]);
+            if (pass == 2) acc1[j] = ffma2(v1, g2, acc1[j]);
+          } else {
+            if (pass == 0) acc0[j] = ffma2(v0, h2, acc0[j]);
+            if (pass == 2) acc0[j] = ffma2(v1, g2, acc0[j]);
+          }
         }
       }
     }
@@ -201,6 +214,184 @@ conv_strided_tile_kernel(const float* __restrict__ in0, const float* __restrict_
         }
       }
     }
+  }
+}
+
+// Marching variant of the strided sweep (the default for radii <= 20): a CTA owns
+// COLS columns of one outer slice and walks the whole filtered axis in steps of
+// STEP = NB*G outputs, keeping the input rows it needs in a shared-memory ring.
+// Every input row is read from L2/HBM exactly once (the tile kernel re-reads its 2R
+// halo rows per tile), and the cp.async copies of the NEXT step's rows are in
+// flight while the current step is computed, so the FMA pipe never waits on a tile
+// load.  One __syncthreads per step.
+//
+// Ring geometry is kept in units of 8 rows: RP = R rounded up to 8, RING = 2 RP +
+// 2 STEP rows, slot of global row a = (a + RP) mod RING.  A thread's window starts
+// at a multiple of 8, so each block of 8 window rows wraps as a whole and the wrap
+// costs one select per 8 rows (the shared loads use immediate offsets from one of
+// two base pointers).  Rows between R and RP are loaded but carry no taps.
+// grid = (ceil(inner / COLS), 1, outer), block = G * COLS / 2, 2 CTAs per SM.
+template <int R, int RP, int MODE, int NB, int COLS, int NBLK, int K>
+__device__ __forceinline__ void scatter_rows_ring(const float* const (&b0)[NBLK],
+                                                  const float* const (&b1)[NBLK],
+                                                  float2 (&acc0)[NB], float2 (&acc1)[NB],
+                                                  const LogWeights& w) {
+  // K counts window rows from a_out - RP; taps exist for rows a_out - R .. a_out + NB - 1 + R
+  if constexpr (K < NB + 2 * RP) {
+    constexpr int KT = K - (RP - R);           // row index relative to a_out - R
+    if constexpr (KT >= 0 && KT < NB + 2 * R) {
+      // block base pointer + compile-time offset: one LDS.64 with an immediate
+      const float2 v0 = *reinterpret_cast<const float2*>(b0[K / 8] + K * COLS);
+      float2 v1 = make_float2(0.f, 0.f);
+      if (MODE != MODE_FIRST) v1 = *reinterpret_cast<const float2*>(b1[K / 8] + K * COLS);
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const int t = KT - j;
+        if (t >= 0 && t <= 2 * R) {
+          const int wi = t >= R ? t - R : R - t;
+          const float2 g2 = make_float2(w.g[wi], w.g[wi]);
+          const float2 h2 = make_float2(w.h[wi], w.h[wi]);
+          if (MODE == MODE_FIRST) {
+            acc0[j] = ffma2(v0, g2, acc0[j]);
+            acc1[j] = ffma2(v0, h2, acc1[j]);
+          } else if (MODE == MODE_MID) {
+            acc0[j] = ffma2(v0, g2, acc0[j]);
+            acc1[j] = ffma2(v0, h2, acc1[j]);
+            acc1[j] = ffma2(v1, g2, acc1[j]);
+          } else {
+            acc0[j] = ffma2(v0, h2, acc0[j]);
+            acc0[j] = ffma2(v1, g2, acc0[j]);
+          }
+        }
+      }
+    }
+    scatter_rows_ring<R, RP, MODE, NB, COLS, NBLK, K + 1>(b0, b1, acc0, acc1, w);
+  }
+}
+
+template <int R, int MODE, int NB, int G, int COLS>
+__global__ void __launch_bounds__(G * COLS / 2, 2)
+conv_march_kernel(const float* __restrict__ in0, const float* __restrict__ in1,
+                  float* __restrict__ out0, float* __restrict__ out1, int n_axis,
+                  int64_t inner, int64_t outer_stride, const __grid_constant__ LogWeights w,
+                  float scale) {
+  constexpr int PAIRS = COLS / 2;
+  constexpr int THREADS = G * PAIRS;
+  constexpr int STEP = NB * G;
+  constexpr int RP = (R + 7) / 8 * 8;
+  constexpr int RING = 2 * RP + 2 * STEP;
+  constexpr int NBLK = (NB + 2 * RP) / 8;      // 8-row blocks in a thread's window
+  constexpr int CH = COLS / 4;                 // 16-byte chunks per row
+  constexpr int RPT = THREADS / CH;            // rows covered by one pass of the CTA
+  static_assert(THREADS % CH == 0 && STEP % RPT == 0 && (2 * RP) % RPT == 0, "load geometry");
+  static_assert(NB % 8 == 0 && STEP % 8 == 0, "ring geometry is in units of 8 rows");
+  extern __shared__ __align__(16) float ring[];
+  float* r0 = ring;
+  float* r1 = ring + RING * COLS;
+  const int tid = threadIdx.x;
+  const int64_t c0 = (int64_t)blockIdx.x * COLS;
+  const int64_t base = (int64_t)blockIdx.z * outer_stride + c0;
+  const int ncols = (int)((inner - c0) < COLS ? (inner - c0) : COLS);   // multiple of 4
+  const int lch = (tid % CH) * 4;              // this thread's 16-byte column chunk
+  const bool lact = lch < ncols;
+
+  // loader state: next row this thread copies, its ring slot, its global pointers
+  int la = -RP + tid / CH;
+  int lslot = tid / CH;
+  const int64_t lstride = (int64_t)RPT * inner;
+  const float* lg0 = in0 + base + lch + (int64_t)la * inner;   // dereferenced only when 0 <= la < n_axis
+  const float* lg1 = (MODE != MODE_FIRST ? in1 : in0) + base + lch + (int64_t)la * inner;
+
+  // the next `count` rows (a multiple of RPT) of both inputs -> their ring slots
+  auto load_rows = [&](int count) {
+    const int a_first = la - tid / CH;                                   // CTA-uniform
+    const bool interior = a_first >= 0 && a_first + count <= n_axis;
+    if (lact) {
+      if (interior) {
+        for (int i = 0; i < count / RPT; ++i) {
+          __pipeline_memcpy_async(r0 + lslot * COLS + lch, lg0, 16);
+          if (MODE != MODE_FIRST) __pipeline_memcpy_async(r1 + lslot * COLS + lch, lg1, 16);
+          lg0 += lstride;
+          lg1 += lstride;
+          lslot += RPT;
+          if (lslot >= RING) lslot -= RING;
+        }
+      } else {
+        for (int i = 0; i < count / RPT; ++i) {
+          const int64_t g = base + lch + (int64_t)reflect_index(la + RPT * i, n_axis) * inner;
+          __pipeline_memcpy_async(r0 + lslot * COLS + lch, in0 + g, 16);
+          if (MODE != MODE_FIRST) __pipeline_memcpy_async(r1 + lslot * COLS + lch, in1 + g, 16);
+          lslot += RPT;
+          if (lslot >= RING) lslot -= RING;
+        }
+        lg0 += (int64_t)(count / RPT) * lstride;
+        lg1 += (int64_t)(count / RPT) * lstride;
+      }
+    }
+    la += count;
+    __pipeline_commit();
+  };
+
+  load_rows(STEP + 2 * RP);
+  const int nsteps = (n_axis + STEP - 1) / STEP;
+  const int grp = tid / PAIRS;
+  const int col = (tid - grp * PAIRS) * 2;
+  int a_out = grp * NB;
+  int cslot = grp * NB;                        // ring slot of input row a_out - RP
+  float* o0 = out0 + base + col + (int64_t)a_out * inner;
+  float* o1 = (MODE != MODE_LAST ? out1 : out0) + base + col + (int64_t)a_out * inner;
+  const int64_t ostep = (int64_t)(STEP - NB) * inner;
+  for (int s = 0; s < nsteps; ++s) {
+    __pipeline_wait_prior(0);
+    __syncthreads();          // this step's rows have landed; step s-1's rows are free
+    if (s + 1 < nsteps) load_rows(STEP);
+    if (a_out < n_axis && col < ncols) {
+      float2 acc0[NB], acc1[NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) { acc0[j] = make_float2(0.f, 0.f); acc1[j] = make_float2(0.f, 0.f); }
+      // a window starts at a multiple of 8 rows, so each 8-row block wraps as a whole
+      const float* b0[NBLK];
+      const float* b1[NBLK];
+#pragma unroll
+      for (int i = 0; i < NBLK; ++i) {
+        const int sl = cslot + 8 * i < RING ? cslot : cslot - RING;
+        b0[i] = r0 + sl * COLS + col;
+        b1[i] = r1 + sl * COLS + col;
+      }
+      scatter_rows_ring<R, RP, MODE, NB, COLS, NBLK, 0>(b0, b1, acc0, acc1, w);
+      if (a_out + NB <= n_axis) {              // full block: no per-row bound checks
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          if (MODE == MODE_LAST) {
+            *reinterpret_cast<float2*>(o0) = make_float2(acc0[j].x * scale, acc0[j].y * scale);
+          } else {
+            *reinterpret_cast<float2*>(o0) = acc0[j];
+            *reinterpret_cast<float2*>(o1) = acc1[j];
+            o1 += inner;
+          }
+          o0 += inner;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          if (a_out + j < n_axis) {
+            if (MODE == MODE_LAST) {
+              *reinterpret_cast<float2*>(o0) = make_float2(acc0[j].x * scale, acc0[j].y * scale);
+            } else {
+              *reinterpret_cast<float2*>(o0) = acc0[j];
+              *reinterpret_cast<float2*>(o1) = acc1[j];
+            }
+          }
+          o0 += inner;
+          if (MODE != MODE_LAST) o1 += inner;
+        }
+      }
+      o0 += ostep;
+      if (MODE != MODE_LAST) o1 += ostep;
+    }
+    a_out += STEP;
+    cslot += STEP;
+    if (cslot >= RING) cslot -= RING;
   }
 }
 
@@ -309,8 +500,12 @@ int launch_x_first(int r, const float* in, float* outA, float* outB, int64_t nro
 
 // Radius buckets with a compiled kernel; a request is served by the smallest
 // bucket >= r (taps beyond r carry zero weight).
+#ifdef MMB_DEV_BUCKETS      /* quick developer builds: the radii of sigma 3..5 only */
+#define MMB_RADIUS_BUCKETS(X) X(12) X(16) X(20)
+#else
 #define MMB_RADIUS_BUCKETS(X) \
   X(2) X(4) X(6) X(8) X(10) X(12) X(13) X(14) X(15) X(16) X(17) X(18) X(19) X(20) \
   X(24) X(32) X(48) X(64)
+#endif
 
 }  // namespace mmb

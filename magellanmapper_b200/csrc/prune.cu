@@ -159,6 +159,67 @@ prune_resolve_kernel(const int* __restrict__ n_ptr, int n_max, const int2* __res
   for (int v = threadIdx.x; v < n; v += blockDim.x) keep[v] = state[v] == 1 ? 1 : 0;
 }
 
+// ---- counting sort of the candidates by z plane -------------------------------------
+// The pair search only has to look 2*sigma_max*sqrt(3)+1 planes up once the
+// candidates are listed by ascending z (prune_edges_kernel's z_sorted path); local
+// maxima arrive in atomic order, so they are bucketed by plane first: histogram,
+// single-CTA exclusive scan, scatter.  The order inside a plane is arbitrary - the
+// kill-graph resolution does not depend on the listing order.
+__global__ void z_hist_kernel(const mmb_cand* __restrict__ cand, const int* __restrict__ n_ptr,
+                              int n_max, int* __restrict__ hist) {
+  const int n = min(*n_ptr, n_max);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(&hist[cand[i].z], 1);
+}
+
+__global__ void __launch_bounds__(1024)
+z_scan_kernel(int* __restrict__ hist, int Z) {
+  __shared__ int part[1024];
+  const int per = (Z + 1023) / 1024;
+  const int lo = threadIdx.x * per, hi = min(Z, lo + per);
+  int sum = 0;
+  for (int z = lo; z < hi; ++z) sum += hist[z];
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {          // Hillis-Steele inclusive scan
+    const int v = threadIdx.x >= d ? part[threadIdx.x - d] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int run = part[threadIdx.x] - sum;             // exclusive prefix of this thread's range
+  for (int z = lo; z < hi; ++z) {
+    const int c = hist[z];
+    hist[z] = run;
+    run += c;
+  }
+}
+
+__global__ void z_scatter_kernel(const mmb_cand* __restrict__ cand, const int* __restrict__ n_ptr,
+                                 int n_max, int* __restrict__ cursor,
+                                 mmb_cand* __restrict__ out) {
+  const int n = min(*n_ptr, n_max);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const mmb_cand c = cand[i];
+    out[atomicAdd(&cursor[c.z], 1)] = c;
+  }
+}
+
+// cand[0 .. min(*n_ptr, n_max)) -> out, listed by ascending z; hist = Z ints of scratch
+int sort_by_z_enqueue(const mmb_cand* cand, const int* n_ptr, int n_max, int Z, int* hist,
+                      mmb_cand* out, cudaStream_t st) {
+  if (n_max <= 0) return MMB_OK;
+  MMB_CHECK_CUDA(cudaMemsetAsync(hist, 0, (size_t)Z * sizeof(int), st));
+  z_hist_kernel<<<(unsigned)cdiv(n_max, 256), 256, 0, st>>>(cand, n_ptr, n_max, hist);
+  MMB_CHECK_LAUNCH();
+  z_scan_kernel<<<1, 1024, 0, st>>>(hist, Z);
+  MMB_CHECK_LAUNCH();
+  z_scatter_kernel<<<(unsigned)cdiv(n_max, 256), 256, 0, st>>>(cand, n_ptr, n_max, hist, out);
+  MMB_CHECK_LAUNCH();
+  return MMB_OK;
+}
+
 int make_ladder(const double* sigmas_host, int num_sigma, SigmaLadder* out) {
   if (num_sigma < 1 || num_sigma > kMaxSigmas) {
     set_error("num_sigma %d outside 1..%d", num_sigma, kMaxSigmas);

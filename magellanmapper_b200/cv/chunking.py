@@ -127,13 +127,17 @@ def merge_split_stack2(sub_rois: np.ndarray, overlap, offset: int, output) -> No
 def merge_blobs(blob_rois: np.ndarray) -> Optional[np.ndarray]:
     """Stack every chunk's blob table, tagging rows with the chunk coordinate in
     three extra trailing columns; ``None`` when no chunk has blobs."""
-    parts = []
-    for c in np.ndindex(*blob_rois.shape):
-        blobs = blob_rois[c]
-        if blobs is None:
-            continue
-        tagged = np.empty((blobs.shape[0], blobs.shape[1] + 3), dtype=np.result_type(blobs, int))
-        tagged[:, :-3] = blobs
-        tagged[:, -3:] = c
-        parts.append(tagged)
-    return np.vstack(parts) if parts else None
+    cells = [(c, blob_rois[c]) for c in np.ndindex(*blob_rois.shape) if blob_rois[c] is not None]
+    if not cells:
+        return None
+    n_rows = sum(b.shape[0] for _, b in cells)
+    n_cols = cells[0][1].shape[1]
+    # one allocation, filled chunk by chunk (no per-chunk temporaries, no vstack copy)
+    out = np.empty((n_rows, n_cols + 3), dtype=np.result_type(*[b.dtype for _, b in cells], int))
+    at = 0
+    for c, blobs in cells:
+        n = blobs.shape[0]
+        out[at:at + n, :-3] = blobs
+        out[at:at + n, -3:] = c
+        at += n
+    return out

@@ -267,9 +267,15 @@ class StackPruner(object):
                        channels, overlap_padding=None):
         """Prune axis by axis.  For each seam the slab ``[end - (overlap + pad),
         end + pad)`` of chunk ``j`` is pruned (chunk ``j`` = master, ``j + 1`` =
-        check); blobs outside every slab pass through; the next axis works on
-        the recombined table.  Returns ``(table without chunk tags, DataFrame of
-        pruning ratios)`` or ``(None, None)``."""
+        check, ``prune_overlap``); blobs outside every slab pass through; the next
+        axis works on the recombined table.  Returns ``(table without chunk tags,
+        DataFrame of pruning ratios)`` or ``(None, None)``.
+
+        Same arithmetic and row order as ``prune_overlap`` applied seam by seam
+        (``tests/test_host_mirror.py`` checks that), but carried out on row
+        INDICES plus the three narrow arrays that matter (positions, chunk tags,
+        absolute coordinates): the wide table is gathered once at the end instead
+        of being copied for every seam of every axis."""
         merged = chunking.merge_blobs(seg_rois)
         if merged is None:
             return None, None
@@ -277,19 +283,22 @@ class StackPruner(object):
             overlap_padding = tol
         cols = ("blobs", "ratio_pruning", "ratio_adjacent")
         ratios_out = {}
-        per_channel = []
+        abs_inds = detector.Blobs._get_abs_inds()
+        rel = np.ascontiguousarray(merged[:, :3])
+        abs_zyx = np.ascontiguousarray(merged[:, abs_inds])
+        tags = np.ascontiguousarray(merged[:, -3:]).astype(np.int64)
+        chl_col = detector.Blobs.get_blobs_channel(merged)
         last = tuple(np.subtract(sub_roi_slices.shape, 1))
+        order = []
         for chl in channels:
-            blobs = detector.Blobs.blobs_in_channel(merged, chl)
+            cur = np.flatnonzero(np.isin(chl_col, chl))
             for axis in range(3):
                 n_sec = sub_rois_offsets.shape[axis]
                 if n_sec <= 1:
                     continue
-                # row selections are kept as index arrays over a contiguous copy of
-                # the coordinate column; the wide table is gathered once per axis
-                pos = np.ascontiguousarray(blobs[:, axis])
-                keep_idx = []
-                work = []
+                pos = rel[cur, axis]
+                tag = tags[cur, axis]
+                keep_parts, seam_parts = [], []
                 for j in range(n_sec):
                     coord = [0, 0, 0]
                     coord[axis] = j
@@ -299,35 +308,44 @@ class StackPruner(object):
                     size = sl[axis].stop - sl[axis].start
                     end = start + size
                     shift = overlap[axis] + overlap_padding[axis]
-                    blobs_ol = None
-                    n_next = None
                     if j < n_sec - 1:
                         lo, hi = end - shift, end + overlap_padding[axis]
-                        blobs_ol = blobs[np.flatnonzero((pos >= lo) & (pos < hi))]
+                        in_slab = np.flatnonzero((pos >= lo) & (pos < hi))
                         # same-sized region just past the slab, for the ratio metric
+                        n_next = None
                         nlo = end + tol[axis]
                         nhi = nlo + overlap[axis] + 2 * overlap_padding[axis]
                         total = sub_rois_offsets[last][axis] + size
                         if nlo < total and nhi < total:
                             n_next = int(np.count_nonzero((pos >= nlo) & (pos < nhi)))
+                        # chunk j = master, chunk j + 1 = check, any other chunk dropped
+                        master = cur[in_slab[tag[in_slab] == j]]
+                        check = cur[in_slab[tag[in_slab] == j + 1]]
+                        if len(master) and len(check):
+                            m_last, hit = detector._find_close_blobs(rel[check], rel[master], tol)
+                            sel = m_last >= 0
+                            if np.any(sel):
+                                abs_zyx[master[sel]] = np.around(
+                                    (abs_zyx[master[sel]] + abs_zyx[check[m_last[sel]]]) / 2)
+                            check = check[~hit]
+                        seam_parts.append(master)
+                        seam_parts.append(check)
+                        if n_next is not None:
+                            ratios = detector.meas_pruning_ratio(
+                                len(in_slab), len(master) + len(check), n_next)
+                            if ratios:
+                                for c, v in zip(cols, ratios):
+                                    ratios_out.setdefault(c, []).append(v)
                         upper = lo
                     else:
                         upper = end
                     lower = start + (shift if j > 0 else 0)
-                    keep_idx.append(np.flatnonzero((pos < upper) & (pos >= lower)))
-                    work.append((blobs_ol, axis, tol, n_next))
-                cls.blobs_to_prune = work
-                pruned_parts = []
-                for j in range(len(work)):
-                    res, ratios = cls.prune_overlap_by_index(j)
-                    if res is not None:
-                        pruned_parts.append(res)
-                    if ratios:
-                        for c, v in zip(cols, ratios):
-                            ratios_out.setdefault(c, []).append(v)
-                blobs = np.concatenate([blobs[np.concatenate(keep_idx)]] + pruned_parts)
-            per_channel.append(blobs)
-        out = np.vstack(per_channel)[:, :-3]
+                    keep_parts.append(cur[np.flatnonzero((pos < upper) & (pos >= lower))])
+                cur = np.concatenate(keep_parts + seam_parts)
+            order.append(cur)
+        order = order[0] if len(order) == 1 else np.concatenate(order)
+        out = merged[order, :-3]
+        out[:, abs_inds] = abs_zyx[order]
         return out, pd.DataFrame(ratios_out)
 
 

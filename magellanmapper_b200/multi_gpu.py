@@ -118,10 +118,14 @@ def exchange_planes(local: torch.Tensor, held: Sequence[Range], wanted: Sequence
     if (w0, w1) == (h0, h1):
         ext = local
     else:
-        ext = torch.empty((w1 - w0,) + tuple(local.shape[1:]), dtype=local.dtype,
+        ext = torch.empty((max(0, w1 - w0),) + tuple(local.shape[1:]), dtype=local.dtype,
                           device=local.device)
-        ext[h0 - w0:h1 - w0].copy_(local)
+        a, b = max(w0, h0), min(w1, h1)          # the part of the wanted range held here
+        if a < b:
+            ext[a - w0:b - w0].copy_(local[a - h0:b - h0])
     if world == 1:
+        if not (h0 <= w0 and w1 <= h1) and w1 > w0:
+            raise ValueError(f"planes {wanted[rank]} are not all held ({held[rank]})")
         return ext
     ops, keep = [], []
     for src, dst, z0, z1 in transfer_plan(held, wanted):
@@ -310,6 +314,70 @@ def seamless_plan(n_planes: int, world: int, block_depth: int, halo_planes: int)
     return own, ext
 
 
+def _seamless_setup(global_shape, channel):
+    from .cv import detector, stack_detect
+    from .plot import plot_3d
+    from .settings import config
+    settings = config.get_roi_profile(channel)
+    Z, Y, X = (int(v) for v in global_shape[:3])
+    blocks = stack_detect.setup_blocks(settings, (Z, Y, X))
+    scale = detector.calc_scaling_factor()[2]
+    dms = blocks.denoise_max_shape
+    pre = plot_3d.preproc_params(settings, channel) if dms is not None else None
+    sigmas = detector.sigma_ladder(settings, scale, False)
+    halo = int(4.0 * float(np.max(sigmas)) + 0.5) + 1          # r_max + 1
+    bd = (int(dms[0]), int(dms[1]), int(dms[2])) if dms is not None else (1, 1, 1)
+    return settings, pre, sigmas, halo, bd
+
+
+def seamless_candidates(ext, ext_range: Range, own_range: Range, global_shape: Sequence[int],
+                        channel: int = 0, tile_yx: Optional[Sequence[int]] = None) -> np.ndarray:
+    """The local part of ``detect_seamless``: local maxima (no pruning) of the
+    planes ``own_range`` given the planes ``ext_range`` (own + halo) of the volume,
+    in GLOBAL coordinates, as ``gpu.CAND_DTYPE`` records."""
+    from . import gpu
+    settings, pre, sigmas, halo, bd = _seamless_setup(global_shape, channel)
+    Z, Y, X = (int(v) for v in global_shape[:3])
+    e0, e1 = ext_range
+    z0, z1 = own_range
+    if z1 <= z0:
+        return np.zeros(0, dtype=gpu.CAND_DTYPE)
+    if e0 % bd[0] != 0 or (e1 % bd[0] != 0 and e1 != Z):
+        raise ValueError(f"extended range {ext_range} is not aligned to the block depth {bd[0]}")
+    if (z0 - e0 < halo and e0 > 0) or (e1 - z1 < halo and e1 < Z):
+        raise ValueError(f"halo of {ext_range} around {own_range} is thinner than {halo} planes")
+    in_scale = 1.0
+    if pre is None:
+        probe = gpu.as_source(ext, channel if ext.dim() == 4 else None)
+        in_scale = {gpu._lib.MMB_U8: 1 / 255.0, gpu._lib.MMB_U16: 1 / 65535.0}.get(probe.dtype, 1.0)
+    ty, tx = (Y, X) if tile_yx is None else (int(tile_yx[0]), int(tile_yx[1]))
+    ty = -(-ty // bd[1]) * bd[1]
+    tx = -(-tx // bd[2]) * bd[2]
+    hy = -(-halo // bd[1]) * bd[1]
+    hx = -(-halo // bd[2]) * bd[2]
+    det = gpu.ChunkDetector((e1 - e0, min(Y, ty + 2 * hy), min(X, tx + 2 * hx)))
+    cands = []
+    for y0 in range(0, Y, ty):
+        for x0 in range(0, X, tx):
+            ya, yb = max(0, y0 - hy), min(Y, y0 + ty + hy)
+            xa, xb = max(0, x0 - hx), min(X, x0 + tx + hx)
+            view = ext[:, ya:yb, xa:xb]
+            src = gpu.as_source(view, channel if ext.dim() == 4 else None)
+            # overlap 1.0 = no pruning here: _prune_blobs runs once over all slabs
+            got, _ = det.detect(src, sigmas, settings["detection_threshold"], 1.0,
+                                scale=in_scale, pre=pre, block_shape=bd,
+                                z_lo=z0 - e0, z_hi=z1 - e0)
+            if len(got):
+                yy, xx = got["y"] + ya, got["x"] + xa
+                keep = (yy >= y0) & (yy < min(Y, y0 + ty)) & (xx >= x0) & (xx < min(X, x0 + tx))
+                got = got[keep].copy()
+                got["z"] += e0
+                got["y"] += ya
+                got["x"] += xa
+                cands.append(got)
+    return np.concatenate(cands) if cands else np.zeros(0, dtype=gpu.CAND_DTYPE)
+
+
 def detect_seamless(slab, held: Sequence[Range], global_shape: Sequence[int],
                     channel: int = 0, group=None, tile_yx: Optional[Sequence[int]] = None):
     """Detect blobs as if the whole volume were ONE chunk (no chunk seams).
@@ -318,71 +386,26 @@ def detect_seamless(slab, held: Sequence[Range], global_shape: Sequence[int],
     slab without pruning and keep the local maxima of the planes it owns
     (``z_lo``/``z_hi`` of ``mmb_detect_chunk_enqueue``); rank 0: gather the
     candidates and run ``_prune_blobs`` once over all of them
-    (``mmb_prune_within``).  ``tile_yx`` additionally tiles y and x inside a rank
-    (tile + halo must fit the workspace of eight float volumes).
+    (``mmb_prune_within_zsorted``).  ``tile_yx`` additionally tiles y and x inside
+    a rank (tile + halo must fit the workspace of eight float volumes).
 
     Returns on rank 0 the ``(n, 11)`` blob table of ``detector.detect_blobs`` in
-    ``peak_local_max`` order, None elsewhere.
+    ``peak_local_max`` order (None if empty), None elsewhere.
     """
     from . import gpu
-    from .cv import detector, stack_detect
-    from .plot import plot_3d
-    from .settings import config
     rank, world = _world(group)
-    settings = config.get_roi_profile(channel)
+    settings, pre, sigmas, halo, bd = _seamless_setup(global_shape, channel)
     Z, Y, X = (int(v) for v in global_shape[:3])
-    blocks = stack_detect.setup_blocks(settings, (Z, Y, X))
-    scale = detector.calc_scaling_factor()[2]
-    dms = blocks.denoise_max_shape
-    pre = plot_3d.preproc_params(settings, channel) if dms is not None else None
-    sigmas = detector.sigma_ladder(settings, scale, False)
-    r_max = int(4.0 * float(np.max(sigmas)) + 0.5)
-    halo = r_max + 1
-    bd = (int(dms[0]), int(dms[1]), int(dms[2])) if dms is not None else (1, 1, 1)
     own, ext_ranges = seamless_plan(Z, world, bd[0], halo)
-    # the caller's slabs need not coincide with the aligned owned slabs
-    ext = exchange_planes(slab, held, ext_ranges, group) if world > 1 or tuple(
-        held[rank]) != tuple(ext_ranges[rank]) else slab
-    e0, e1 = ext_ranges[rank]
-    z0, z1 = own[rank]
-    in_scale = 1.0
-    cands = []
-    if z1 > z0:
-        src_full = gpu.as_source(ext, channel if ext.dim() == 4 else None)
-        if pre is None:
-            in_scale = {gpu._lib.MMB_U8: 1 / 255.0, gpu._lib.MMB_U16: 1 / 65535.0}.get(
-                src_full.dtype, 1.0)
-        ty, tx = (Y, X) if tile_yx is None else (int(tile_yx[0]), int(tile_yx[1]))
-        ty = -(-ty // bd[1]) * bd[1]
-        tx = -(-tx // bd[2]) * bd[2]
-        hy = -(-halo // bd[1]) * bd[1]
-        hx = -(-halo // bd[2]) * bd[2]
-        det = None
-        for y0 in range(0, Y, ty):
-            for x0 in range(0, X, tx):
-                ya, yb = max(0, y0 - hy), min(Y, y0 + ty + hy)
-                xa, xb = max(0, x0 - hx), min(X, x0 + tx + hx)
-                view = ext[:, ya:yb, xa:xb] if ext.dim() == 3 else ext[:, ya:yb, xa:xb, :]
-                src = gpu.as_source(view, channel if ext.dim() == 4 else None)
-                if det is None:
-                    det = gpu.ChunkDetector((e1 - e0, min(Y, ty + 2 * hy), min(X, tx + 2 * hx)))
-                got, _ = det.detect(src, sigmas, settings["detection_threshold"], 1.0,
-                                    scale=in_scale, pre=pre, block_shape=bd,
-                                    z_lo=z0 - e0, z_hi=z1 - e0)
-                if len(got):
-                    yy, xx = got["y"] + ya, got["x"] + xa
-                    keep = (yy >= y0) & (yy < min(Y, y0 + ty)) & (xx >= x0) & (xx < min(X, x0 + tx))
-                    got = got[keep].copy()
-                    got["z"] += e0
-                    got["y"] += ya
-                    got["x"] += xa
-                    cands.append(got)
-    mine = np.concatenate(cands) if cands else np.zeros(0, dtype=gpu.CAND_DTYPE)
-    raw = mine.view(np.int32).reshape(-1, 5)
+    # the caller's slabs need not coincide with the block-aligned owned slabs
+    ext = exchange_planes(slab, held, ext_ranges, group)
+    mine = seamless_candidates(ext, ext_ranges[rank], own[rank], (Z, Y, X), channel, tile_yx)
+    raw = np.ascontiguousarray(mine).view(np.int32).reshape(-1, 5)
     parts = gather_rows(raw, 5, group, dtype=np.int32)
     if rank != 0:
         return None
-    allc = np.concatenate(parts).astype(np.int32).reshape(-1).view(gpu.CAND_DTYPE)
+    allc = np.ascontiguousarray(np.concatenate(parts).astype(np.int32)).reshape(-1).view(
+        gpu.CAND_DTYPE)
     return prune_global(allc, sigmas, settings["overlap"], (Z, Y, X), channel)
 
 

@@ -184,3 +184,99 @@ def test_errors_match_reference():
         stack_detect.detect_blobs_stack("x", None)
     with pytest.raises(ValueError):
         stack_detect.detect_blobs_blocks("x", np_io.Image5d(None))
+
+
+def _np_find_close(blobs, master, tol):
+    """numpy stand-in for the GPU box match (same contract as detector._find_close_blobs)."""
+    c = np.asarray(blobs)[:, :3].astype(np.int32)
+    m = np.asarray(master)[:, :3].astype(np.int32)
+    close = np.all(np.abs(m[:, None, :] - c[None, :, :]) <= np.asarray(tol)[None, None, :], axis=2)
+    hit = close.any(axis=0)
+    last = np.where(close.any(axis=1), close.shape[1] - 1 - np.argmax(close[:, ::-1], axis=1), -1)
+    return last.astype(np.int64), hit
+
+
+def _prune_seam_by_seam(seg_rois, blocks, channels):
+    """prune_blobs_mp spelled out with StackPruner.prune_overlap on the wide table,
+    seam by seam, the way the reference structures it (stack_detect.py:680-861)."""
+    merged = chunking.merge_blobs(seg_rois)
+    overlap, tol, pad = blocks.overlap, blocks.tol, blocks.overlap_padding
+    slices, offsets = blocks.sub_roi_slices, blocks.sub_rois_offsets
+    last = tuple(np.subtract(slices.shape, 1))
+    per_channel, ratios_all = [], []
+    for chl in channels:
+        blobs = detector.Blobs.blobs_in_channel(merged, chl)
+        for axis in range(3):
+            n_sec = offsets.shape[axis]
+            if n_sec <= 1:
+                continue
+            pos = blobs[:, axis]
+            keep_idx, work = [], []
+            for j in range(n_sec):
+                coord = [0, 0, 0]
+                coord[axis] = j
+                coord = tuple(coord)
+                start = offsets[coord][axis]
+                size = slices[coord][axis].stop - slices[coord][axis].start
+                end = start + size
+                shift = overlap[axis] + pad[axis]
+                blobs_ol, n_next = None, None
+                if j < n_sec - 1:
+                    lo, hi = end - shift, end + pad[axis]
+                    blobs_ol = blobs[(pos >= lo) & (pos < hi)]
+                    nlo = end + tol[axis]
+                    nhi = nlo + overlap[axis] + 2 * pad[axis]
+                    total = offsets[last][axis] + size
+                    if nlo < total and nhi < total:
+                        n_next = int(np.count_nonzero((pos >= nlo) & (pos < nhi)))
+                    upper = lo
+                else:
+                    upper = end
+                lower = start + (shift if j > 0 else 0)
+                keep_idx.append(np.flatnonzero((pos < upper) & (pos >= lower)))
+                work.append((blobs_ol, axis, tol, n_next))
+            parts = []
+            for j, w in enumerate(work):
+                res, ratios = stack_detect.StackPruner.prune_overlap(j, w)
+                if res is not None:
+                    parts.append(res)
+                if ratios:
+                    ratios_all.append(ratios)
+            blobs = np.concatenate([blobs[np.concatenate(keep_idx)]] + parts)
+        per_channel.append(blobs)
+    return np.vstack(per_channel)[:, :-3], ratios_all
+
+
+def test_prune_blobs_mp_index_form_equals_seam_by_seam(monkeypatch):
+    """The index-array implementation of prune_blobs_mp against prune_overlap applied
+    seam by seam on the wide table: same rows, same order, same averaged positions,
+    same ratios - on a 3x3x2 chunk grid crowded with near-duplicates at the seams."""
+    monkeypatch.setattr(detector, "_find_close_blobs", _np_find_close)
+    _roi_blobs(segment_size=40)
+    config.resolutions = [[1.0, 1.0, 1.0]]
+    shape = (100, 110, 70)
+    blocks = stack_detect.setup_blocks(config.roi_profile, shape)
+    rng = np.random.default_rng(11)
+    seg = np.empty(blocks.sub_roi_slices.shape, dtype=object)
+    for c in np.ndindex(*seg.shape):
+        sl = blocks.sub_roi_slices[c]
+        size = [s.stop - s.start for s in sl]
+        n = int(rng.integers(0, 60))
+        if n == 0:
+            seg[c] = None
+            continue
+        zyx = np.column_stack([rng.integers(0, s, n) for s in size]).astype(float)
+        t = detector.Blobs(np.column_stack([zyx, np.full(n, 6.0)])).format_blobs(int(n % 2))
+        detector.Blobs.shift_blob_rel_coords(t, blocks.sub_rois_offsets[c])
+        detector.Blobs.shift_blob_abs_coords(t, blocks.sub_rois_offsets[c])
+        seg[c] = t
+    for channels in ([0], [0, 1]):
+        want, want_ratios = _prune_seam_by_seam(seg, blocks, channels)
+        got, df = stack_detect.StackPruner.prune_blobs_mp(
+            None, seg, blocks.overlap, blocks.tol, blocks.sub_roi_slices,
+            blocks.sub_rois_offsets, channels, blocks.overlap_padding)
+        np.testing.assert_array_equal(got, want)
+        assert len(df) == len(want_ratios)
+        if len(df):
+            np.testing.assert_allclose(df.to_numpy(), np.array(want_ratios))
+    assert len(want) < sum(len(seg[c]) for c in np.ndindex(*seg.shape) if seg[c] is not None)

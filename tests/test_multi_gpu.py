@@ -1,0 +1,254 @@
+"""Multi-GPU host logic: slab / chunk-row geometry, the halo exchange and the
+variable-length gathers (world size 2 on gloo, CPU tensors), and - on a GPU -
+the two shardings against the single-GPU results they must reproduce."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+import torch.distributed as dist                               # noqa: E402
+import torch.multiprocessing as mp                             # noqa: E402
+
+from magellanmapper_b200 import multi_gpu as mg               # noqa: E402
+from magellanmapper_b200.cv import chunking, stack_detect     # noqa: E402
+from magellanmapper_b200.settings import config, roi_prof     # noqa: E402
+
+
+def _setup(resolution=(1, 1, 1), near_max=-1.0, **mods):
+    prof = roi_prof.ROIProfile()
+    prof.add_profiles("roi_blobs.yaml")
+    for k, v in mods.items():
+        prof[k] = v
+    config.roi_profile = prof
+    config.roi_profiles = [prof]
+    config.resolutions = [list(resolution)]
+    config.near_max = [near_max]
+    config.channel = None
+    return prof
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+# ---- geometry ---------------------------------------------------------------------
+
+def test_slab_bounds_partition_and_alignment():
+    for Z, world, align in ((1024, 2, 25), (4096, 8, 25), (100, 8, 25), (2048, 8, 1), (7, 3, 5)):
+        b = mg.slab_bounds(Z, world, align)
+        assert len(b) == world and b[0][0] == 0 and b[-1][1] == Z
+        for (a0, a1), (b0, b1) in zip(b[:-1], b[1:]):
+            assert a1 == b0 and a0 <= a1
+            assert a1 % align == 0
+    assert mg.slab_bounds(1024, 2, 25) == [(0, 500), (500, 1024)]
+
+
+def test_chunk_rows_follow_first_plane_and_wanted_ranges():
+    """config-2 stacks piled up as one 4-rank volume: 512-plane slabs, 500-plane
+    chunk pitch with 5 planes of overlap (chunking.stack_splitter)."""
+    _setup()
+    held = mg.slab_bounds(2048, 4)
+    blocks = stack_detect.setup_blocks(config.roi_profile, (2048, 2048, 2048))
+    rows, z_bounds, wanted = mg.chunk_row_plan((2048, 2048, 2048), blocks, held)
+    assert z_bounds == [(0, 505), (500, 1005), (1000, 1505), (1500, 2005), (2000, 2048)]
+    assert rows == [[0, 1], [2], [3], [4]]
+    assert wanted == [(0, 1005), (512, 1505), (1024, 2005), (1536, 2048)]
+    plan = mg.transfer_plan(held, wanted)
+    # planes only ever travel from a later slab to an earlier rank
+    assert all(src > dst for src, dst, _, _ in plan)
+    assert (1, 0, 512, 1005) in plan and (2, 1, 1024, 1505) in plan
+
+
+def test_seamless_plan_halo_is_whole_block_layers():
+    own, ext = mg.seamless_plan(1024, 2, 25, 21)
+    assert own == [(0, 500), (500, 1024)] and ext == [(0, 525), (475, 1024)]
+    own, ext = mg.seamless_plan(2048, 8, 25, 21)
+    for (a, b), (ea, eb) in zip(own, ext):
+        assert ea % 25 == 0 and (eb % 25 == 0 or eb == 2048)
+        assert (a - ea >= 21 or ea == 0) and (eb - b >= 21 or eb == 2048)
+
+
+def test_pack_unpack_tables_roundtrip():
+    rng = np.random.default_rng(5)
+    grid = (2, 3, 2)
+    seg = np.empty(grid, dtype=object)
+    for c in np.ndindex(*grid):
+        n = int(rng.integers(0, 4))
+        seg[c] = rng.random((n, 11)) if n else None
+    packed = chunking.merge_blobs(seg)
+    half = len(packed) // 2
+    # a cut in the middle of one chunk's rows (as if two ranks held the halves)
+    back = mg.unpack_tables([packed[:0], packed], grid)
+    for c in np.ndindex(*grid):
+        if seg[c] is None:
+            assert back[c] is None
+        else:
+            np.testing.assert_array_equal(back[c], seg[c])
+    assert half >= 0
+
+
+# ---- collectives on gloo, world size 2 -----------------------------------------------
+
+def _gloo_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        vol = torch.arange(40 * 3 * 4, dtype=torch.int16).reshape(40, 3, 4)
+        held = [(0, 17), (17, 40)]
+        wanted = [(0, 25), (10, 40)]
+        ext = mg.exchange_planes(vol[held[rank][0]:held[rank][1]].clone(), held, wanted)
+        assert torch.equal(ext, vol[wanted[rank][0]:wanted[rank][1]])
+        # a rank that wants nothing still serves its planes
+        wanted2 = [(0, 40), (20, 20)]
+        ext2 = mg.exchange_planes(vol[held[rank][0]:held[rank][1]].clone(), held, wanted2)
+        assert torch.equal(ext2, vol[wanted2[rank][0]:wanted2[rank][1]])
+        # variable-length gathers (float64 tables and int32 candidate records)
+        mine = np.full((3 + 2 * rank, 14), float(rank)) + np.arange(14)
+        parts = mg.gather_rows(mine if rank == 0 else mine, 14)
+        cand = (np.arange(5 * (rank + 1), dtype=np.int32) + 100 * rank).reshape(-1, 5)
+        cparts = mg.gather_rows(cand if rank == 1 else None, 5, dtype=np.int32)
+        if rank == 0:
+            assert [p.shape for p in parts] == [(3, 14), (5, 14)]
+            np.testing.assert_array_equal(parts[1], np.full((5, 14), 1.0) + np.arange(14))
+            assert cparts[0].shape == (0, 5) and cparts[1].dtype == np.int32
+            np.testing.assert_array_equal(cparts[1], cand * 0 + (np.arange(10) + 100).reshape(2, 5))
+        else:
+            assert parts is None and cparts is None
+        assert mg._agree_max(7 + rank) == 8
+        open(os.path.join(out_dir, f"ok{rank}"), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_exchange_and_gather_gloo_world2(tmp_path):
+    port = _free_port()
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
+
+
+# ---- GPU: both shardings against the single-GPU results ----------------------------------
+
+@pytest.mark.gpu
+def test_slab_driver_world1_equals_reference_vectors(golden_dir, tmp_path):
+    from magellanmapper_b200 import gpu
+    gpu.require_cuda()
+    g = np.load(os.path.join(golden_dir, "stack_small.npz"))
+    _setup(near_max=float(g["near_max"]), segment_size=50)
+    config.filename = str(tmp_path / "slab")
+    os.chdir(tmp_path)
+    vol = torch.from_numpy(g["vol"].view(np.int16)).cuda()
+    _, _, blobs = mg.detect_blobs_blocks_slabs(config.filename, vol, [(0, vol.shape[0])],
+                                               vol.shape)
+    np.testing.assert_array_equal(blobs.blobs, g["plain_blobs"])
+    stack_detect.StackDetector.release_workspace()
+
+
+@pytest.mark.gpu
+def test_slab_driver_chunk_rows_on_shifted_slabs(golden_dir, tmp_path):
+    """Each 'rank' of a two-slab split run in turn on one GPU (planes handed over
+    by slicing instead of send/recv): the union of the per-rank chunk tables,
+    seam-pruned, equals the reference's output."""
+    from magellanmapper_b200 import gpu
+    from magellanmapper_b200.cv import detector
+    gpu.require_cuda()
+    g = np.load(os.path.join(golden_dir, "stack_small.npz"))
+    _setup(near_max=float(g["near_max"]), segment_size=50)
+    vol = torch.from_numpy(g["vol"].view(np.int16)).cuda()
+    Z = vol.shape[0]
+    held = mg.slab_bounds(Z, 2)
+    blocks = stack_detect.setup_blocks(config.roi_profile, tuple(vol.shape))
+    rows, z_bounds, wanted = mg.chunk_row_plan(vol.shape, blocks, held)
+    assert sorted(rows[0] + rows[1]) == list(range(blocks.sub_roi_slices.shape[0]))
+    grid = blocks.sub_roi_slices.shape
+    parts = []
+    for rank in range(2):
+        w0, w1 = wanted[rank]
+        ext = vol[w0:w1]
+        local = np.empty(grid, dtype=object)
+        coords = []
+        for c in np.ndindex(*grid):
+            sz, sy, sx = blocks.sub_roi_slices[c]
+            if c[0] in rows[rank]:
+                local[c] = (slice(sz.start - w0, sz.stop - w0), sy, sx)
+                coords.append(c)
+            else:
+                local[c] = (slice(0, 0),) * 3
+        seg = stack_detect.StackDetector.detect_blobs_sub_rois(
+            None, ext, local, blocks.sub_rois_offsets, blocks.denoise_max_shape,
+            blocks.exclude_border, False, [0], coords=coords)
+        parts.append(mg.pack_tables(seg))
+    seg_all = mg.unpack_tables(parts, grid)
+    table, _ = stack_detect.StackPruner.prune_blobs_mp(
+        None, seg_all, blocks.overlap, blocks.tol, blocks.sub_roi_slices,
+        blocks.sub_rois_offsets, [0], blocks.overlap_padding)
+    blobs = detector.Blobs(table)
+    blobs.replace_rel_with_abs_blob_coords(table)
+    blobs.blobs = table
+    np.testing.assert_array_equal(blobs.remove_abs_blob_coords(True), g["plain_blobs"])
+    stack_detect.StackDetector.release_workspace()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tile_yx", [None, (50, 75)])
+def test_seamless_slabs_equal_one_chunk(tile_yx):
+    """Three z-slabs with block-aligned halos (and optionally y/x tiles inside each
+    slab), candidates pooled and pruned once == the whole volume detected as a
+    single chunk: identical blob table, row for row."""
+    from magellanmapper_b200 import gpu, synth
+    from magellanmapper_b200.cv import detector
+    gpu.require_cuda()
+    shape = (160, 140, 150)
+    vol, _ = synth.make_volume(shape, seed=77, density=1 / 2500.0)
+    nm = synth.near_max_of(vol)
+    _setup(near_max=nm)
+    settings, pre, sigmas, halo, bd = mg._seamless_setup(shape, 0)
+    assert halo == 21 and bd == (25, 25, 25)
+    dev = torch.from_numpy(vol.view(np.int16)).cuda()
+    det = gpu.ChunkDetector(shape)
+    whole, _ = det.detect(gpu.as_source(dev), sigmas, settings["detection_threshold"],
+                          settings["overlap"], pre=pre, block_shape=bd)
+    want = detector.cands_to_blobs(whole, sigmas, shape[1:], 0)
+    own, ext = mg.seamless_plan(shape[0], 3, bd[0], halo)
+    cands = [mg.seamless_candidates(dev[e0:e1], (e0, e1), o, shape, 0, tile_yx)
+             for o, (e0, e1) in zip(own, ext)]
+    got = mg.prune_global(np.concatenate(cands), sigmas, settings["overlap"], shape, 0)
+    assert len(want) > 50
+    np.testing.assert_array_equal(got, want)
+
+
+def _nccl_worker(rank, world, port, out_dir, golden_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        g = np.load(os.path.join(golden_dir, "stack_small.npz"))
+        _setup(near_max=float(g["near_max"]), segment_size=50)
+        os.chdir(out_dir)
+        vol = torch.from_numpy(g["vol"].view(np.int16))
+        held = mg.slab_bounds(vol.shape[0], world)
+        slab = vol[held[rank][0]:held[rank][1]].cuda()
+        _, _, blobs = mg.detect_blobs_blocks_slabs(os.path.join(out_dir, "nccl"), slab, held,
+                                                   vol.shape)
+        if rank == 0:
+            np.testing.assert_array_equal(blobs.blobs, g["plain_blobs"])
+        else:
+            assert blobs is None
+        open(os.path.join(out_dir, f"ok{rank}"), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_slab_driver_nccl_world2(golden_dir, tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    port = _free_port()
+    mp.spawn(_nccl_worker, args=(2, port, str(tmp_path), golden_dir), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
