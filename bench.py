@@ -366,14 +366,31 @@ def main():
                            "gbps": (alg_bytes[k] * units[i] / (ms[i] * 1e-3) / 1e9
                                     if k in alg_bytes else None)}
     dom = max((k for k in per_kind if k in alg_bytes), key=lambda k: per_kind[k]["ms"])
+    # DRAM traffic of the dominant kernel from the committed ncu capture (bytes per
+    # voxel measured on one 505^3 chunk), scaled to this run's average launch size
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic_v3.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        if dom in tj["kernels"]:
+            vox_per_launch = units[kinds.index(dom)] / per_kind[dom]["launches"]
+            traffic = tj["kernels"][dom]["dram_bytes_per_voxel"] * vox_per_launch
+            traffic_src = ("dram__bytes_read.sum + dram__bytes_write.sum per voxel from "
+                           "profiles/r01_traffic_v3.json x this run's voxels per launch")
     roof = {"bound": "hbm", "kernel": dom, "achieved": per_kind[dom]["gbps"],
             "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": per_kind[dom]["gbps"] / peaks["hbm_gbs"], "traffic": None,
+            "frac": per_kind[dom]["gbps"] / peaks["hbm_gbs"], "traffic": traffic,
+            "traffic_source": traffic_src,
+            "algorithmic_bytes_per_launch": alg_bytes[dom] * units[kinds.index(dom)]
+            / per_kind[dom]["launches"],
             "peak_source": f"{peak_src} copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
             "avg_launch_ms": per_kind[dom]["ms"] / per_kind[dom]["launches"],
             "algorithmic_bytes_per_voxel": alg_bytes[dom],
-            "fp32_colimit": "sweeps issue (14 r + 7) FFMA per voxel per scale, r = 12..20: "
-                            "FP32-issue bound before HBM bound (DESIGN.md)",
+            "fp32_colimit": "the three sweeps execute (14 r + 7) fp32 FMAs per voxel per scale "
+                            "(r = 12..20) as packed FFMA2; at the 128 lane-FMA/clk/SM pipe peak "
+                            "that alone takes as long as moving the algorithmic bytes at the "
+                            "measured HBM peak (DESIGN.md section 4)",
             "per_kernel": per_kind}
 
     cpu = None

@@ -6,8 +6,6 @@ namespace mmb {
 constexpr int kNB = 16;
 constexpr int kThreads = 128;
 
-constexpr int kCols = 128;
-constexpr int kTileThreads = 256;
 
 template <int R>
 static int run(const float* in0, const float* in1, float* out0, float* out1, int n_axis,
@@ -15,47 +13,8 @@ static int run(const float* in0, const float* in1, float* out0, float* out1, int
                cudaStream_t st) {
   // outer == 1 is the z sweep (whole y-x plane contiguous), otherwise the y sweep
   ProfScope ps(outer == 1 ? PROF_LOG_Z : PROF_LOG_Y, (double)inner * n_axis * outer, st);
-  const uintptr_t bits = (uintptr_t)in0 | (uintptr_t)in1 | (uintptr_t)out0 | (uintptr_t)out1;
-  const bool aligned = (bits & 15) == 0 && inner % 4 == 0;
-  if constexpr (R <= 20) {
-    if (aligned) {
-      // marching kernel: ring of 2*RP + 2*STEP rows of both inputs, 2 CTAs per SM
-      constexpr int G = MMB_MARCH_G, NBM = MMB_MARCH_NB;
-      constexpr size_t smem = (size_t)2 * (2 * ((R + 7) / 8 * 8) + 2 * NBM * G) * kCols * sizeof(float);
-      auto kern = conv_march_kernel<R, 0, NBM, G, kCols>;
-      static bool configured = false;
-      if (!configured) {
-        MMB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)smem));
-        configured = true;
-      }
-      dim3 grid((unsigned)cdiv(inner, kCols), 1, (unsigned)outer);
-      kern<<<grid, G * kCols / 2, smem, st>>>(in0, in1, out0, out1, n_axis, inner,
-                                              (int64_t)n_axis * inner, w, scale);
-      MMB_CHECK_LAUNCH();
-      return MMB_OK;
-    }
-  }
-  if constexpr (R > 20) {
-    if (aligned) {
-      constexpr int NSEGS = R <= 24 ? 4 : 2;
-      constexpr int ROWS = kNB * NSEGS + 2 * R;
-      constexpr int NARR = 0 == 0 ? 1 : 2;
-      constexpr size_t smem = (size_t)NARR * ROWS * kCols * sizeof(float);
-      auto kern = conv_strided_tile_kernel<R, 0, kNB, NSEGS, kCols, kTileThreads>;
-      static bool configured = false;
-      if (!configured) {
-        MMB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)smem));
-        configured = true;
-      }
-      dim3 grid((unsigned)cdiv(inner, kCols), (unsigned)cdiv(n_axis, kNB * NSEGS), (unsigned)outer);
-      kern<<<grid, kTileThreads, smem, st>>>(in0, in1, out0, out1, n_axis, inner,
-                                             (int64_t)n_axis * inner, w, scale);
-      MMB_CHECK_LAUNCH();
-      return MMB_OK;
-    }
-  }
+  // MODE_FIRST along a strided axis is not on the detector's path (x is always the
+  // first sweep); mmb_log_pass still offers it, served by the direct kernel only
   {
     dim3 grid((unsigned)cdiv(inner, kThreads), (unsigned)cdiv(n_axis, kNB), (unsigned)outer);
     conv_strided_kernel<R, 0, kNB, kThreads><<<grid, kThreads, 0, st>>>(

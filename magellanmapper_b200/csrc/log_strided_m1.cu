@@ -36,7 +36,7 @@ static int run(const float* in0, const float* in1, float* out0, float* out1, int
       return MMB_OK;
     }
   }
-  if constexpr (R > 20) {
+  if constexpr (R > 20 && R <= 32) {      // wider radii: direct kernel below
     if (aligned) {
       constexpr int NSEGS = R <= 24 ? 4 : 2;
       constexpr int ROWS = kNB * NSEGS + 2 * R;
