@@ -28,6 +28,12 @@ from ..settings import config, roi_prof
 _logger = config.logger.getChild(__name__)
 
 
+#: keep per-chunk blob tables on the device and seam-prune them there
+#: (``device_tables``); False routes everything through the host tables of the
+#: reference's structure (``detect_blobs_sub_rois`` + ``prune_blobs_mp``)
+DEVICE_TABLES = True
+
+
 class StackTimes(Enum):
     """Keys of ``stack_detection_times.csv``."""
     DETECTION = "Detection"
@@ -176,6 +182,45 @@ class StackDetector(object):
             detector.Blobs.shift_blob_rel_coords(segments, offset)
             detector.Blobs.shift_blob_abs_coords(segments, offset)
         return coord, segments
+
+    @classmethod
+    def detect_blobs_sub_rois_device(cls, img, sub_roi_slices, sub_rois_offsets,
+                                     denoise_max_shape, channel, coords=None):
+        """``detect_blobs_sub_rois`` with the per-chunk tables left on the device:
+        returns the merged (N, 14) float64 CUDA tensor of
+        ``device_tables.ChunkTables.merged`` (None when nothing was found) instead
+        of an object array of host tables.  No ``exclude_border`` support (the
+        caller falls back to the host route for that)."""
+        from collections import deque
+        from .. import gpu
+        from . import device_tables
+        last_coord = np.subtract(sub_roi_slices.shape, 1)
+        img = gpu.upload_if_fits(img)
+        largest = [max(s[a].stop - s[a].start for s in sub_roi_slices.flat) for a in range(3)]
+        det = cls._workspace(tuple(largest))
+        n_chl = len(plot_3d.setup_channels(img, channel, 3)[1])
+        if n_chl > det.n_slots - 1:
+            cls._gpu_detector = None
+            cls._gpu_detector = det = gpu.ChunkDetector(det.max_shape, n_slots=2 * n_chl)
+        tables = device_tables.ChunkTables(det.device)
+        pending = deque()
+
+        def finish_oldest():
+            coord, offset, _, _, shape, det_, tickets = pending.popleft()
+            for chl, sigmas, ticket in tickets:
+                cand, _ = det_.collect_device(ticket)
+                tables.append(cand, coord, offset, shape[1:3], sigmas, chl)
+
+        todo = np.ndindex(*sub_roi_slices.shape) if coords is None else [tuple(c) for c in coords]
+        for coord in todo:
+            while pending and cls._workspace(tuple(largest)).free_slots() < n_chl:
+                finish_oldest()
+            pending.append(cls.enqueue_sub_roi(
+                coord, sub_rois_offsets[coord], last_coord, denoise_max_shape, None,
+                img[sub_roi_slices[coord]], channel, False))
+        while pending:
+            finish_oldest()
+        return tables.merged()
 
     @classmethod
     def detect_blobs_sub_rois(cls, img5d, img, sub_roi_slices, sub_rois_offsets,
@@ -394,16 +439,28 @@ def detect_blobs_blocks(filename_base: str, img5d: np_io.Image5d,
         _, channels = plot_3d.setup_channels(roi, channels, 3)
     settings = config.get_roi_profile(channels[0])
     blocks = setup_blocks(settings, roi.shape)
-    seg_rois = StackDetector.detect_blobs_sub_rois(
-        img5d, roi, blocks.sub_roi_slices, blocks.sub_rois_offsets,
-        blocks.denoise_max_shape, blocks.exclude_border, coloc, channels)
-    detection_time = time() - t_det
-
-    t_prune = time()
-    segments_all, df_pruning = StackPruner.prune_blobs_mp(
-        roi, seg_rois, blocks.overlap, blocks.tol, blocks.sub_roi_slices,
-        blocks.sub_rois_offsets, channels, blocks.overlap_padding)
-    pruning_time = time() - t_prune
+    if blocks.exclude_border is None and DEVICE_TABLES and not coloc:
+        # per-chunk tables stay in HBM; merged, seam-pruned there, one copy back
+        from . import device_tables
+        merged = StackDetector.detect_blobs_sub_rois_device(
+            roi, blocks.sub_roi_slices, blocks.sub_rois_offsets, blocks.denoise_max_shape,
+            channels)
+        detection_time = time() - t_det
+        t_prune = time()
+        segments_all, df_pruning = device_tables.prune_merged(
+            merged, blocks.overlap, blocks.tol, blocks.sub_roi_slices,
+            blocks.sub_rois_offsets, channels, blocks.overlap_padding)
+        pruning_time = time() - t_prune
+    else:
+        seg_rois = StackDetector.detect_blobs_sub_rois(
+            img5d, roi, blocks.sub_roi_slices, blocks.sub_rois_offsets,
+            blocks.denoise_max_shape, blocks.exclude_border, coloc, channels)
+        detection_time = time() - t_det
+        t_prune = time()
+        segments_all, df_pruning = StackPruner.prune_blobs_mp(
+            roi, seg_rois, blocks.overlap, blocks.tol, blocks.sub_roi_slices,
+            blocks.sub_rois_offsets, channels, blocks.overlap_padding)
+        pruning_time = time() - t_prune
 
     if df_pruning is not None and save_dfs and len(df_pruning.columns):
         df_pruning.to_csv("blob_ratios.csv", index=False)

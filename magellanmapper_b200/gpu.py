@@ -321,6 +321,25 @@ class ChunkDetector:
         slot.busy = False
         return out, n_peaks
 
+    def collect_device(self, ticket: Ticket) -> Tuple[torch.Tensor, int]:
+        """Like ``collect`` but the survivors stay on the device: returns ``((n, 5)
+        int32 tensor of candidate records, number of local maxima)``.  Only the
+        three status counters cross to the host."""
+        slot = ticket.slot
+        ticket.event.synchronize()
+        n_peaks, n_out, n_edges, _ = (int(v) for v in slot.status_host)
+        edge_cap = self.lib.mmb_detect_edge_capacity(slot.capacity)
+        if n_peaks > slot.capacity or n_edges > edge_cap:
+            slot.busy = False
+            need = max(n_peaks, (n_edges - 4096) // 4 + 1)
+            self.capacity = max(self.capacity, int(need * 1.25) + 1024)
+            self._alloc()
+            return self.collect_device(self.enqueue(*ticket.args))
+        # stream-ordered copy: the slot may be reused by a later chunk right away
+        out = slot.cand[:n_out].clone()
+        slot.busy = False
+        return out, n_peaks
+
     def detect(self, src: Source, sigmas: Sequence[float], threshold: float, overlap: float,
                scale: float = 1.0, pre: Optional[MmbPreprocParams] = None,
                block_shape: Sequence[int] = (25, 25, 25), z_lo: int = 0,

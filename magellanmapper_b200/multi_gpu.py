@@ -7,11 +7,11 @@ sub-ROIs are spread over GPUs.  Two shardings:
 
 * **chunk-faithful z-slabs** (``detect_blobs_blocks_slabs``): the volume lives
   as contiguous z-slabs, one per rank.  The reference's chunk grid
-  (``chunking.stack_splitter``) is laid over the WHOLE volume; chunk z-rows are
-  dealt to the rank holding their first plane, the planes a chunk row needs
-  from other slabs (its 5-voxel overlap, and whatever the 500-voxel chunk
-  pitch leaves on the far side of a slab face) arrive by ``send/recv`` between
-  slab neighbours, chunks run independently, the per-chunk tables are gathered
+  (``chunking.stack_splitter``) is laid over the WHOLE volume; contiguous runs of
+  chunk z-rows are dealt to the ranks so that the largest run is as small as
+  possible, the planes a run needs from other slabs (the 5-voxel overlap, and
+  whatever the 500-voxel chunk pitch leaves on the far side of a slab face)
+  arrive by ``send/recv`` between slab neighbours, chunks run independently, the per-chunk tables are gathered
   to rank 0 (sizes, then payload) and ``StackPruner.prune_blobs_mp`` removes
   the seam duplicates there.  Row for row equal to the single-GPU result.
 * **seamless z-slabs** (``detect_seamless``): the volume is one chunk.  Each
@@ -62,6 +62,40 @@ def assign_chunk_rows(z_starts: Sequence[int], held: Sequence[Range]) -> List[Li
     rows: List[List[int]] = [[] for _ in held]
     for k, z in enumerate(z_starts):
         rows[owner_of(int(z), held)].append(k)
+    return rows
+
+
+def assign_chunk_rows_balanced(z_bounds: Sequence[Range], world: int) -> List[List[int]]:
+    """Contiguous runs of chunk z-rows, one run per rank, minimising the largest
+    number of planes any rank filters (the chunk pitch rarely divides the slab
+    depth: 512-plane slabs against 500-plane chunks would otherwise leave the last
+    rank with the 24-plane remainder and the first with two full rows).  Runs are
+    contiguous and in rank order so halo planes only ever travel between slab
+    neighbours."""
+    n = len(z_bounds)
+    cost = [b - a for a, b in z_bounds]
+    pre = [0]
+    for c in cost:
+        pre.append(pre[-1] + c)
+    INF = float("inf")
+    # best[k][i] = minimal achievable maximum when the first i rows go to k ranks
+    best = [[INF] * (n + 1) for _ in range(world + 1)]
+    cut = [[0] * (n + 1) for _ in range(world + 1)]
+    best[0][0] = 0
+    for k in range(1, world + 1):
+        for i in range(0, n + 1):
+            for j in range(0, i + 1):
+                if best[k - 1][j] == INF:
+                    continue
+                v = max(best[k - 1][j], pre[i] - pre[j])
+                if v < best[k][i] or (v == best[k][i] and j > cut[k][i]):
+                    best[k][i], cut[k][i] = v, j
+    rows: List[List[int]] = [[] for _ in range(world)]
+    i = n
+    for k in range(world, 0, -1):
+        j = cut[k][i]
+        rows[k - 1] = list(range(j, i))
+        i = j
     return rows
 
 
@@ -130,12 +164,13 @@ def exchange_planes(local: torch.Tensor, held: Sequence[Range], wanted: Sequence
     ops, keep = [], []
     for src, dst, z0, z1 in transfer_plan(held, wanted):
         if src == rank:
-            buf = local[z0 - h0:z1 - h0].contiguous()
+            # planes travel as raw bytes: NCCL has no 16-bit integer type
+            buf = local[z0 - h0:z1 - h0].contiguous().view(torch.uint8)
             keep.append(buf)
             ops.append(dist.P2POp(dist.isend, buf, dist.get_global_rank(group, dst)
                                   if group is not None else dst, group))
         elif dst == rank:
-            view = ext[z0 - w0:z1 - w0]            # contiguous: whole planes
+            view = ext[z0 - w0:z1 - w0].view(torch.uint8)      # contiguous: whole planes
             ops.append(dist.P2POp(dist.irecv, view, dist.get_global_rank(group, src)
                                   if group is not None else src, group))
     if ops:
@@ -178,6 +213,38 @@ def gather_rows(rows: Optional[np.ndarray], n_cols: int, group=None, dst: int = 
     return None
 
 
+def gather_tensor_rows(rows: Optional[torch.Tensor], n_cols: int, group=None, dst: int = 0,
+                       dtype=torch.float64, device=None) -> Optional[List[torch.Tensor]]:
+    """``gather_rows`` for tables that already live on the communication device
+    (CUDA tensors under NCCL): no host staging on either side."""
+    rank, world = _world(group)
+    dev = device if device is not None else (rows.device if rows is not None else
+                                             _comm_device(group))
+    mine = torch.zeros((0, n_cols), dtype=dtype, device=dev) if rows is None else \
+        rows.to(dtype).reshape(-1, n_cols).contiguous()
+    if world == 1:
+        return [mine]
+    count = torch.tensor([mine.shape[0]], dtype=torch.int64, device=dev)
+    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(counts, count, group=group)
+    counts = [int(c.item()) for c in counts]
+    g = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+    if rank == dst:
+        out = []
+        for r in range(world):
+            if r == rank:
+                out.append(mine)
+            else:
+                buf = torch.empty((counts[r], n_cols), dtype=dtype, device=dev)
+                if counts[r]:
+                    dist.recv(buf, src=g(r), group=group)
+                out.append(buf)
+        return out
+    if mine.shape[0]:
+        dist.send(mine, dst=g(dst), group=group)
+    return None
+
+
 def pack_tables(seg_rois: np.ndarray) -> Optional[np.ndarray]:
     """Flatten a chunk-grid object array of blob tables into one table with the
     chunk coordinate in three trailing columns (``chunking.merge_blobs``)."""
@@ -208,8 +275,15 @@ def chunk_row_plan(global_shape: Sequence[int], blocks, held: Sequence[Range]):
     grid = blocks.sub_roi_slices.shape
     z_bounds = [(blocks.sub_roi_slices[k, 0, 0][0].start, blocks.sub_roi_slices[k, 0, 0][0].stop)
                 for k in range(grid[0])]
-    rows = assign_chunk_rows([b[0] for b in z_bounds], held)
-    wanted = [wanted_range(rows[r], z_bounds, held[r]) for r in range(len(held))]
+    rows = assign_chunk_rows_balanced(z_bounds, len(held))
+    # a rank asks only for the planes of its chunk rows (not for its whole slab)
+    wanted = []
+    for r in range(len(held)):
+        if rows[r]:
+            wanted.append((min(z_bounds[k][0] for k in rows[r]),
+                           max(z_bounds[k][1] for k in rows[r])))
+        else:
+            wanted.append((held[r][0], held[r][0]))
     return rows, z_bounds, wanted
 
 
@@ -255,24 +329,37 @@ def detect_blobs_blocks_slabs(filename_base: str, slab, held: Sequence[Range],
     for c in np.ndindex(*grid):
         if local_slices[c] is None:
             local_slices[c] = (slice(0, 0), slice(0, 0), slice(0, 0))
-    seg_rois = None
-    if coords:
-        seg_rois = stack_detect.StackDetector.detect_blobs_sub_rois(
-            None, ext, local_slices, blocks.sub_rois_offsets, blocks.denoise_max_shape,
-            blocks.exclude_border, False, channels, coords=coords)
-    packed = pack_tables(seg_rois) if seg_rois is not None else None
-    n_cols = len(detector.Blobs.Cols) + 3 if hasattr(detector.Blobs, "Cols") else 14
-    if packed is not None:
-        n_cols = packed.shape[1]
-    n_cols = _agree_max(n_cols, group)
-    parts = gather_rows(packed, n_cols, group)
-    if rank != 0:
-        return None, None, None
-
-    seg_all = unpack_tables(parts, grid)
-    segments_all, df_pruning = stack_detect.StackPruner.prune_blobs_mp(
-        None, seg_all, blocks.overlap, blocks.tol, blocks.sub_roi_slices,
-        blocks.sub_rois_offsets, channels, blocks.overlap_padding)
+    if blocks.exclude_border is None and stack_detect.DEVICE_TABLES:
+        # device-resident tables: the gather moves CUDA tensors over NVLink and rank 0
+        # prunes the seams on its GPU
+        from .cv import device_tables
+        merged = None
+        if coords:
+            merged = stack_detect.StackDetector.detect_blobs_sub_rois_device(
+                ext, local_slices, blocks.sub_rois_offsets, blocks.denoise_max_shape,
+                channels, coords=coords)
+        parts = gather_tensor_rows(merged, device_tables.N_MERGED, group, device=slab.device)
+        if rank != 0:
+            return None, None, None
+        # runs of chunk rows are contiguous and in rank order = chunk-grid order
+        segments_all, df_pruning = device_tables.prune_merged(
+            torch.cat(parts), blocks.overlap, blocks.tol, blocks.sub_roi_slices,
+            blocks.sub_rois_offsets, channels, blocks.overlap_padding)
+    else:
+        seg_rois = None
+        if coords:
+            seg_rois = stack_detect.StackDetector.detect_blobs_sub_rois(
+                None, ext, local_slices, blocks.sub_rois_offsets, blocks.denoise_max_shape,
+                blocks.exclude_border, False, channels, coords=coords)
+        packed = pack_tables(seg_rois) if seg_rois is not None else None
+        n_cols = _agree_max(14 if packed is None else packed.shape[1], group)
+        parts = gather_rows(packed, n_cols, group)
+        if rank != 0:
+            return None, None, None
+        seg_all = unpack_tables(parts, grid)
+        segments_all, df_pruning = stack_detect.StackPruner.prune_blobs_mp(
+            None, seg_all, blocks.overlap, blocks.tol, blocks.sub_roi_slices,
+            blocks.sub_rois_offsets, channels, blocks.overlap_padding)
     filename_blobs = libmag.combine_paths(filename_base, config.SUFFIX_BLOBS)
     blobs = detector.Blobs(segments_all, path=filename_blobs)
     if segments_all is not None:

@@ -164,3 +164,29 @@ def test_stack_accepts_device_tensor(golden_dir, tmp_path):
     _, _, blobs = stack_detect.detect_blobs_blocks(
         config.filename, np_io.Image5d(t), None, None, [0], False, False, True)
     np.testing.assert_array_equal(blobs.blobs, g["plain_blobs"])
+
+
+def test_device_tables_equal_host_tables(golden_dir, tmp_path, monkeypatch):
+    """The device-resident route (tables merged and seam-pruned in HBM) and the
+    host route through the reference's structure give the same table, row for
+    row, and the same pruning-ratio frame - one channel and two channels."""
+    g = np.load(os.path.join(golden_dir, "stack_small.npz"))
+    os.chdir(tmp_path)
+    vol = g["vol"]
+    two = np.stack([vol, vol[::-1, :, ::-1]], axis=-1)
+    for img, chls in ((vol, [0]), (two, [0, 1])):
+        outs = []
+        for flag in (True, False):
+            monkeypatch.setattr(stack_detect, "DEVICE_TABLES", flag)
+            _setup(near_max=float(g["near_max"]), segment_size=50)
+            config.near_max = [float(g["near_max"])] * len(chls)
+            config.filename = str(tmp_path / f"dt{int(flag)}")
+            _, _, blobs = stack_detect.detect_blobs_blocks(
+                config.filename, np_io.Image5d(img[None]), None, None, chls, False, True, True)
+            ratios = np.loadtxt(tmp_path / "blob_ratios.csv", delimiter=",", skiprows=1)
+            outs.append((blobs.blobs, ratios))
+        np.testing.assert_array_equal(outs[0][0], outs[1][0])
+        np.testing.assert_array_equal(outs[0][1], outs[1][1])
+        assert len(outs[0][0]) > 100
+    np.testing.assert_array_equal(outs[0][0][outs[0][0][:, 6] == 0][:5],
+                                  outs[1][0][outs[1][0][:, 6] == 0][:5])

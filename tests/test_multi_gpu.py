@@ -47,7 +47,7 @@ def test_slab_bounds_partition_and_alignment():
     assert mg.slab_bounds(1024, 2, 25) == [(0, 500), (500, 1024)]
 
 
-def test_chunk_rows_follow_first_plane_and_wanted_ranges():
+def test_chunk_rows_balanced_and_wanted_ranges():
     """config-2 stacks piled up as one 4-rank volume: 512-plane slabs, 500-plane
     chunk pitch with 5 planes of overlap (chunking.stack_splitter)."""
     _setup()
@@ -55,12 +55,20 @@ def test_chunk_rows_follow_first_plane_and_wanted_ranges():
     blocks = stack_detect.setup_blocks(config.roi_profile, (2048, 2048, 2048))
     rows, z_bounds, wanted = mg.chunk_row_plan((2048, 2048, 2048), blocks, held)
     assert z_bounds == [(0, 505), (500, 1005), (1000, 1505), (1500, 2005), (2000, 2048)]
-    assert rows == [[0, 1], [2], [3], [4]]
-    assert wanted == [(0, 1005), (512, 1505), (1024, 2005), (1536, 2048)]
+    assert rows == [[0], [1], [2], [3, 4]]
+    assert wanted == [(0, 505), (500, 1005), (1000, 1505), (1500, 2048)]
     plan = mg.transfer_plan(held, wanted)
-    # planes only ever travel from a later slab to an earlier rank
-    assert all(src > dst for src, dst, _, _ in plan)
-    assert (1, 0, 512, 1005) in plan and (2, 1, 1024, 1505) in plan
+    # halo planes only travel between slab neighbours
+    assert all(abs(src - dst) == 1 for src, dst, _, _ in plan)
+    assert (0, 1, 500, 512) in plan and (1, 2, 1000, 1024) in plan and (2, 3, 1500, 1536) in plan
+    # the first-plane rule (kept for comparison) piles two rows on rank 0
+    assert mg.assign_chunk_rows([b[0] for b in z_bounds], held) == [[0, 1], [2], [3], [4]]
+    # two slabs of config 2: 505 | 505 + 24 planes instead of 1010 | 24
+    b2 = [(0, 505), (500, 1005), (1000, 1024)]
+    assert mg.assign_chunk_rows_balanced(b2, 2) == [[0], [1, 2]]
+    # more ranks than rows: trailing ranks idle, every row assigned once
+    r3 = mg.assign_chunk_rows_balanced(b2, 5)
+    assert sorted(k for r in r3 for k in r) == [0, 1, 2] and max(len(r) for r in r3) == 1
 
 
 def test_seamless_plan_halo_is_whole_block_layers():
