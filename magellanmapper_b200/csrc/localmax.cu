@@ -57,7 +57,7 @@ __device__ __noinline__ bool survives_3d_and_scales(const float* __restrict__ pr
   return true;
 }
 
-__global__ void __launch_bounds__(kLmThreads, 6)
+__global__ void __launch_bounds__(kLmThreads, 8)
 localmax_kernel(const float* __restrict__ prev, const float* __restrict__ cur,
                 const float* __restrict__ next, int Z, int Y, int X, int64_t pitch, int s,
                 float thr, int z_lo, int z_hi, mmb_cand* __restrict__ out, int capacity,
