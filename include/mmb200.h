@@ -59,6 +59,16 @@ typedef struct mmb_preproc_params {
 int mmb_version(void);
 const char* mmb_last_error(void);
 
+/* ---- host -> device feed of a sub-box -----------------------------------------
+ * Replaces the numpy slicing `roi = image5d[0, z0:z1, y0:y1, x0:x1]` /
+ * `cls.img[sub_roi_slices]` that hands a sub-ROI to a worker
+ * (magmap/cv/stack_detect.py:362, :105-107): copies `planes` pieces of
+ * `piece_bytes` contiguous bytes each, `src_pitch_bytes` apart in HOST memory
+ * (pinned for a true asynchronous DMA), to a dense device buffer - e.g. the rows
+ * y0..y1 of every z-plane of a (Z, Y, X) volume.  Asynchronous on `stream`.      */
+int mmb_upload_pieces(void* dst_device, const void* src_host, int64_t planes,
+                      int64_t piece_bytes, int64_t src_pitch_bytes, void* stream);
+
 /* ---- img_as_float ---------------------------------------------------------
  * Replaces skimage.util.img_as_float inside blob_log (reference call site
  * magmap/cv/detector.py:931): out = in * scale, element strides given per axis

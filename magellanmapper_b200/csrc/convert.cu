@@ -54,3 +54,13 @@ extern "C" int mmb_to_float(const void* in, int dtype, const int64_t in_strides[
   return mmb::to_float_impl(in, dtype, in_strides, Z, Y, X, out, pitch, scale,
                             (cudaStream_t)stream);
 }
+
+extern "C" int mmb_upload_pieces(void* dst_device, const void* src_host, int64_t planes,
+                                 int64_t piece_bytes, int64_t src_pitch_bytes, void* stream) {
+  MMB_REQUIRE(dst_device && src_host, "null buffer");
+  MMB_REQUIRE(planes > 0 && piece_bytes > 0 && src_pitch_bytes >= piece_bytes, "bad geometry");
+  MMB_CHECK_CUDA(cudaMemcpy2DAsync(dst_device, (size_t)piece_bytes, src_host,
+                                   (size_t)src_pitch_bytes, (size_t)piece_bytes, (size_t)planes,
+                                   cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return MMB_OK;
+}

@@ -35,13 +35,18 @@ class ChunkTables:
         self.parts: List[torch.Tensor] = []      # (n, 5) int32 candidate records
         self.meta: List[tuple] = []              # (n, coord, offset, (Y, X), sigmas, channel)
 
-    def append(self, cand: torch.Tensor, coord, offset, shape_yx, sigmas, channel: int) -> None:
+    def append(self, cand: torch.Tensor, coord, offset, shape_yx, sigmas, channel: int,
+               grid_rank: Optional[int] = None) -> None:
+        """``grid_rank`` = position of the chunk in the C-ordered chunk grid; chunks
+        may arrive in any order (strip-wise streaming walks y first), the merged
+        table is always in grid order.  Default: arrival order."""
         if cand.shape[0] == 0:
             return
         self.parts.append(cand)
         self.meta.append((int(cand.shape[0]), tuple(int(c) for c in coord),
                           tuple(float(o) for o in offset), (int(shape_yx[0]), int(shape_yx[1])),
-                          np.asarray(sigmas, dtype=np.float64), int(channel)))
+                          np.asarray(sigmas, dtype=np.float64), int(channel),
+                          len(self.meta) if grid_rank is None else int(grid_rank)))
 
     def merged(self) -> Optional[torch.Tensor]:
         """(N, 14) float64 device table in the layout and row order of
@@ -60,9 +65,16 @@ class ChunkTables:
         sig = np.zeros((T, n_sig))
         for i, m in enumerate(self.meta):
             sig[i, :len(m[4])] = m[4]
+        # sort key of a detection: chunk position in the grid, then arrival (channels of
+        # one chunk arrive in request order)
+        seq = sorted(range(T), key=lambda i: (self.meta[i][6], i))
+        place = [0] * T
+        for pos, i in enumerate(seq):
+            place[i] = pos
         per = torch.tensor(
-            [list(m[1]) + list(m[2]) + [m[3][0], m[3][1], len(m[4]), m[5]] for m in self.meta],
-            dtype=torch.float64, device=dev)                     # (T, 10)
+            [list(m[1]) + list(m[2]) + [m[3][0], m[3][1], len(m[4]), m[5], place[i]]
+             for i, m in enumerate(self.meta)],
+            dtype=torch.float64, device=dev)                     # (T, 11)
         sig_t = torch.from_numpy(sig).to(dev)
         row = per[tix]
         z, y, x, s = (cand[:, k].long() for k in range(4))
@@ -72,7 +84,7 @@ class ChunkTables:
         # three stable sorts, least significant key first
         o = torch.sort(lin, stable=True).indices
         o = o[torch.sort(resp[o], descending=True, stable=True).indices]
-        o = o[torch.sort(tix[o], stable=True).indices]
+        o = o[torch.sort(row[:, 10].long()[o], stable=True).indices]
         out = torch.empty((cand.shape[0], N_MERGED), dtype=torch.float64, device=dev)
         zyx = torch.stack((z, y, x), dim=1).double() + row[:, 3:6]
         out[:, 0:3] = zyx

@@ -195,7 +195,23 @@ class StackDetector(object):
         from .. import gpu
         from . import device_tables
         last_coord = np.subtract(sub_roi_slices.shape, 1)
-        img = gpu.upload_if_fits(img)
+        grid = sub_roi_slices.shape
+        todo = list(np.ndindex(*grid)) if coords is None else [tuple(c) for c in coords]
+        # a host image is streamed strip by strip (one strip = every chunk of one y
+        # column) so that uploads overlap the kernels; chunks are then walked in
+        # (y, z, x) order and the table restores the grid order
+        feeder = None
+        if (isinstance(img, np.ndarray) and img.flags.c_contiguous and img.dtype in gpu._NP2MMB
+                and todo):
+            cols = sorted({c[1] for c in todo})
+            y_ranges = []
+            for j in cols:
+                sy = sub_roi_slices[todo[0][0], j, todo[0][2]][1]
+                y_ranges.append((sy.start, sy.stop))
+            feeder = gpu.StripFeeder(img, y_ranges)
+            todo.sort(key=lambda c: (c[1], c[0], c[2]))
+        else:
+            img = gpu.upload_if_fits(img)
         largest = [max(s[a].stop - s[a].start for s in sub_roi_slices.flat) for a in range(3)]
         det = cls._workspace(tuple(largest))
         n_chl = len(plot_3d.setup_channels(img, channel, 3)[1])
@@ -207,17 +223,31 @@ class StackDetector(object):
 
         def finish_oldest():
             coord, offset, _, _, shape, det_, tickets = pending.popleft()
+            rank_in_grid = int(np.ravel_multi_index(coord, grid))
             for chl, sigmas, ticket in tickets:
                 cand, _ = det_.collect_device(ticket)
-                tables.append(cand, coord, offset, shape[1:3], sigmas, chl)
+                tables.append(cand, coord, offset, shape[1:3], sigmas, chl, rank_in_grid)
 
-        todo = np.ndindex(*sub_roi_slices.shape) if coords is None else [tuple(c) for c in coords]
-        for coord in todo:
+        strip_of, strip_dev = None, None
+        for n_done, coord in enumerate(todo):
             while pending and cls._workspace(tuple(largest)).free_slots() < n_chl:
                 finish_oldest()
+            if feeder is not None:
+                j = cols.index(coord[1])
+                if j != strip_of:
+                    if strip_of is not None:
+                        feeder.release(strip_of)
+                    strip_of, strip_dev = j, feeder.strip(j)
+                sz, sy, sx = sub_roi_slices[coord]
+                y0 = feeder.ranges[j][0]
+                sub = strip_dev[sz, sy.start - y0:sy.stop - y0, sx]
+            else:
+                sub = img[sub_roi_slices[coord]]
             pending.append(cls.enqueue_sub_roi(
                 coord, sub_rois_offsets[coord], last_coord, denoise_max_shape, None,
-                img[sub_roi_slices[coord]], channel, False))
+                sub, channel, False))
+        if feeder is not None and strip_of is not None:
+            feeder.release(strip_of)
         while pending:
             finish_oldest()
         return tables.merged()

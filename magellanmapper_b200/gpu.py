@@ -114,6 +114,69 @@ def upload_if_fits(img, fraction: float = 0.4):
     return t.view(torch.uint16) if img.dtype == np.uint16 else t
 
 
+class StripFeeder:
+    """Streams y-strips ``img[:, y0:y1]`` of a C-contiguous HOST array to the device
+    so that the upload of the next strip overlaps the kernels of the current one
+    (a chunk grid is walked strip by strip; a strip holds every chunk of one y
+    column).  Each strip is one pitched DMA (``mmb_upload_pieces``: one contiguous
+    piece per z-plane) on a copy stream into one of two device buffers."""
+
+    def __init__(self, img: np.ndarray, y_ranges: Sequence[Tuple[int, int]], device=None):
+        if not (isinstance(img, np.ndarray) and img.flags.c_contiguous and img.ndim in (3, 4)
+                and img.dtype in _NP2MMB):
+            raise TypeError("StripFeeder needs a C-contiguous (z,y,x[,c]) array of a supported dtype")
+        self.lib = _lib.load()
+        self.device = device or require_cuda()
+        self.img = img
+        self.ranges = [(int(a), int(b)) for a, b in y_ranges]
+        self.tdtype = torch.int16 if img.dtype == np.uint16 else torch.from_numpy(
+            np.zeros(1, img.dtype)).dtype
+        rows = max(b - a for a, b in self.ranges)
+        self.bufs = [torch.empty((img.shape[0], rows) + tuple(img.shape[2:]), dtype=self.tdtype,
+                                 device=self.device) for _ in range(min(2, len(self.ranges)))]
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.uploaded = [None] * len(self.ranges)      # events on the copy stream
+        self.released = [None] * len(self.ranges)      # events on the compute stream
+        for j in range(len(self.bufs)):                # both buffers are free: fill them
+            self._issue(j)
+
+    def _issue(self, j: int) -> None:
+        y0, y1 = self.ranges[j]
+        img = self.img
+        row_bytes = int(np.prod(img.shape[2:])) * img.itemsize
+        buf = self.bufs[j % len(self.bufs)]
+        with torch.cuda.stream(self.copy_stream):
+            if j >= len(self.bufs) and self.released[j - len(self.bufs)] is not None:
+                self.copy_stream.wait_event(self.released[j - len(self.bufs)])
+            src = img.ctypes.data + y0 * row_bytes
+            _lib.check(self.lib.mmb_upload_pieces(
+                C.c_void_p(buf.data_ptr()), C.c_void_p(src), int(img.shape[0]),
+                (y1 - y0) * row_bytes, int(img.shape[1]) * row_bytes,
+                C.c_void_p(self.copy_stream.cuda_stream)))
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        self.uploaded[j] = ev
+
+    def strip(self, j: int) -> torch.Tensor:
+        """Device view of strip ``j`` (shape ``(Z, y1 - y0, X[, C])``); the current
+        stream waits for its upload, and the upload of strip ``j + 1`` is started."""
+        torch.cuda.current_stream().wait_event(self.uploaded[j])
+        y0, y1 = self.ranges[j]
+        buf = self.bufs[j % len(self.bufs)]
+        # dense upload: the buffer is viewed with this strip's own row count
+        n = self.img.shape[0] * (y1 - y0) * int(np.prod(self.img.shape[2:]))
+        return buf.view(-1)[:n].view((self.img.shape[0], y1 - y0) + tuple(self.img.shape[2:]))
+
+    def release(self, j: int) -> None:
+        """Every kernel reading strip ``j`` has been enqueued on the current stream."""
+        ev = torch.cuda.Event()
+        ev.record()
+        self.released[j] = ev
+        nxt = j + len(self.bufs)                       # the strip that reuses this buffer
+        if nxt < len(self.ranges) and self.uploaded[nxt] is None:
+            self._issue(nxt)
+
+
 def to_float(src: Source, scale: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     lib = _lib.load()
     Z, Y, X = src.shape
