@@ -196,6 +196,162 @@ conv_x_tma_kernel(const __grid_constant__ CUtensorMap tm_in,
   if (tid == 0) tma_wait_read<0>();
 }
 
+#ifdef MMB_X_WARP_KERNEL
+// ---- warp-autonomous x sweep (experimental, not the default) -------------------------
+// Measured on B200, 505^3, r = 12/16/20: 0.47/0.49/0.61 ms single-stage (17 warps/SM),
+// 0.48/0.59/0.79 ms with a per-warp two-stage ring (10 warps/SM) - no better than the
+// CTA-synchronous TMA kernel (0.39/0.46/0.56 ms), so the limit of the x sweep is not its
+// barriers; kept for the next round's experiments.
+// conv_x_warp_kernel: every WARP walks its own sequence of 32-row x 32-output tiles
+// with its own two-stage cp.async ring and its own output staging, so nothing in the
+// main loop is CTA-wide: no __syncthreads, no shared barrier, no store drain that a
+// whole CTA waits for.  (The TMA kernel above is CTA-synchronous, three barriers per
+// tile, and sat at 60 % of the FMA pipe whatever its CTA shape.)  Lane = row: a lane
+// reads its (16 + 2R)-float window with 16-byte shared loads - the row pitch is 4 mod
+// 8 floats, which spreads the eight lanes of a quarter-warp over all banks - and
+// scatters it into 16 (A, B) accumulators with FFMA2; two such passes cover the 32
+// outputs.  Results go through a small staging tile so that global stores are
+// 128-byte row segments.  Tiles at an x face (window partly outside the volume) and
+// row tails take a scalar load path with scipy's 'reflect'.
+constexpr int kWTile = 32;                    // outputs per row per tile
+constexpr int kWWarps = 1;                    // warps per CTA: warps are autonomous, so one-warp CTAs pack shared memory best
+constexpr int kWOutPitch = 36;                // staging pitch, floats (4 mod 8)
+#ifndef MMB_XW_STAGES
+#define MMB_XW_STAGES 1
+#endif
+constexpr int kWStages = MMB_XW_STAGES;       // 1: latency hidden by other warps (17 per SM at r = 16); 2: per-warp prefetch
+
+template <int R>
+struct WGeom {
+  static constexpr int R4 = (R + 3) / 4 * 4;
+  static constexpr int WIN = kWTile + 2 * R4;                       // floats per row
+  static constexpr int PITCH = (WIN / 4) % 2 == 1 ? WIN : WIN + 4;  // 4 mod 8
+  static constexpr int STAGE = 32 * PITCH;                          // floats
+  static constexpr int WARP_FLOATS = kWStages * STAGE + 32 * kWOutPitch;
+  static constexpr size_t SMEM = (size_t)kWWarps * WARP_FLOATS * sizeof(float);
+};
+
+template <int R>
+__global__ void __launch_bounds__(32 * kWWarps)
+conv_x_warp_kernel(const float* __restrict__ in, float* __restrict__ outA,
+                   float* __restrict__ outB, int64_t nrows, int X, int64_t pitch, int n_xt,
+                   int n_tiles, const __grid_constant__ LogWeights w) {
+  using G = WGeom<R>;
+  extern __shared__ __align__(16) float wsm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* s_in = wsm + warp * G::WARP_FLOATS;
+  float* s_out = s_in + kWStages * G::STAGE;
+  const int n_warps = gridDim.x * kWWarps;
+  const int gw = blockIdx.x * kWWarps + warp;
+
+  // stage <- tile t (rows r0.., window columns x0 - R4 ..)
+  auto load_tile = [&](int t, int stage) {
+    const int rt = t / n_xt, xt = t - rt * n_xt;
+    const int64_t r0 = (int64_t)rt * 32;
+    const int xs = xt * kWTile - G::R4;
+    float* dst = s_in + stage * G::STAGE;
+    const bool fast = xs >= 0 && xs + G::WIN <= (int)pitch && xs + G::WIN - G::R4 + R <= X &&
+                      r0 + 32 <= nrows;
+    if (fast) {
+      constexpr int CPR = G::WIN / 4;                 // 16-byte chunks per row
+#pragma unroll 4
+      for (int i = lane; i < 32 * CPR; i += 32) {
+        const int rr = i / CPR, c = i - rr * CPR;
+        __pipeline_memcpy_async(dst + rr * G::PITCH + 4 * c,
+                                in + (r0 + rr) * pitch + xs + 4 * c, 16);
+      }
+    } else {
+      // face or tail tile: 16-byte copies wherever a chunk lies inside the row, scalar
+      // loads with scipy's 'reflect' for the few columns outside [0, X)
+      constexpr int CPR = G::WIN / 4;
+      for (int i = lane; i < 32 * CPR; i += 32) {
+        const int rr = i / CPR, c = i - rr * CPR;
+        const int x = xs + 4 * c;
+        float* d = dst + rr * G::PITCH + 4 * c;
+        if (r0 + rr >= nrows) {
+          *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else if (x >= 0 && x + 4 <= X) {
+          __pipeline_memcpy_async(d, in + (r0 + rr) * pitch + x, 16);
+        } else {
+          const float* src = in + (r0 + rr) * pitch;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) d[k] = __ldg(src + reflect_index(x + k, X));
+        }
+      }
+    }
+    __pipeline_commit();
+  };
+
+  int t = gw;
+  if (kWStages == 2 && t < n_tiles) load_tile(t, 0);
+  int stage = 0;
+  for (; t < n_tiles; t += n_warps, stage ^= (kWStages - 1)) {
+    if (kWStages == 2) {
+      const int tn = t + n_warps;
+      if (tn < n_tiles) load_tile(tn, stage ^ 1);
+      else __pipeline_commit();
+      __pipeline_wait_prior(1);              // this tile's copies (all but the newest group)
+    } else {
+      load_tile(t, 0);
+      __pipeline_wait_prior(0);
+    }
+    __syncwarp();
+    const int rt = t / n_xt, xt = t - rt * n_xt;
+    const int64_t r0 = (int64_t)rt * 32;
+    const int x0 = xt * kWTile;
+    const float* row = s_in + stage * G::STAGE + lane * G::PITCH;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      // window of this pass: positions half*16 .. half*16 + 16 + 2*R4 of the row
+      float win[16 + 2 * G::R4];
+#pragma unroll
+      for (int c = 0; c < (16 + 2 * G::R4) / 4; ++c) {
+        const float4 v = *reinterpret_cast<const float4*>(row + half * 16 + 4 * c);
+        win[4 * c + 0] = v.x; win[4 * c + 1] = v.y; win[4 * c + 2] = v.z; win[4 * c + 3] = v.w;
+      }
+      float2 acc[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int i = G::R4 - R; i < G::R4 + 16 + R; ++i) {
+        const float2 vv = make_float2(win[i], win[i]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int tt = i - (G::R4 + j);
+          if (tt >= -R && tt <= R) acc[j] = ffma2(vv, w.gh[tt < 0 ? -tt : tt], acc[j]);
+        }
+      }
+      // A then B through the staging tile: lane = row writes, row-segment reads
+#pragma unroll
+      for (int ab = 0; ab < 2; ++ab) {
+        float* dstg = ab == 0 ? outA : outB;
+        __syncwarp();                         // previous read-back of the staging tile done
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 v = ab == 0
+              ? make_float4(acc[4 * q].x, acc[4 * q + 1].x, acc[4 * q + 2].x, acc[4 * q + 3].x)
+              : make_float4(acc[4 * q].y, acc[4 * q + 1].y, acc[4 * q + 2].y, acc[4 * q + 3].y);
+          *reinterpret_cast<float4*>(s_out + lane * kWOutPitch + 4 * q) = v;
+        }
+        __syncwarp();
+        // 4 lanes cover the 16 floats of a row; 8 rows per instruction
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = i * 8 + (lane >> 2), c4 = lane & 3;
+          const float4 v = *reinterpret_cast<const float4*>(s_out + rr * kWOutPitch + 4 * c4);
+          const int x = x0 + half * 16 + 4 * c4;
+          if (r0 + rr < nrows && x < (int)pitch)
+            *reinterpret_cast<float4*>(dstg + (r0 + rr) * pitch + x) = v;
+        }
+      }
+    }
+    __syncwarp();                             // every lane is done with this stage
+  }
+  __pipeline_wait_prior(0);
+}
+
+#endif  // MMB_X_WARP_KERNEL
+
 constexpr int kNBx = 16;
 constexpr int kNSEG = 8;
 
@@ -206,6 +362,36 @@ static int run_x(const float* in, float* outA, float* outB, int64_t nrows, int X
   const uintptr_t bits = (uintptr_t)in | (uintptr_t)outA | (uintptr_t)outB;
   const bool tma_ok = R <= 24 && (bits & 15) == 0 && pitch % 4 == 0 && X >= 32 && nrows >= 32 &&
                       nrows < (int64_t)1 << 31;
+#ifdef MMB_X_WARP_KERNEL
+  if constexpr (R <= 24) {
+    const int n_xt = (int)cdiv(X, kWTile);
+    const int64_t n_tiles64 = cdiv(nrows, 32) * n_xt;
+    if ((bits & 15) == 0 && pitch % 4 == 0 && X >= 1 && n_tiles64 < ((int64_t)1 << 31)) {
+      using G = WGeom<R>;
+      auto kern = conv_x_warp_kernel<R>;
+      static bool configured = false;
+      static int ctas_per_sm = 1;
+      if (!configured) {
+        MMB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)G::SMEM));
+        MMB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern,
+                                                                     32 * kWWarps, G::SMEM));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        configured = true;
+      }
+      const int64_t want = cdiv(n_tiles64, kWWarps);
+      int64_t full = (int64_t)ctas_per_sm * num_sms();
+      // a warp strides through the tiles by the total warp count: keep that coprime with
+      // the tiles per row so every warp meets its share of the (dearer) x-face tiles
+      auto gcd = [](int64_t a, int64_t b) { while (b) { const int64_t t = a % b; a = b; b = t; } return a; };
+      while (full > 1 && gcd(full * kWWarps, n_xt) != 1) --full;
+      kern<<<(unsigned)(want < full ? want : full), 32 * kWWarps, G::SMEM, st>>>(
+          in, outA, outB, nrows, X, pitch, n_xt, (int)n_tiles64, w);
+      MMB_CHECK_LAUNCH();
+      return MMB_OK;
+    }
+  }
+#endif
   if constexpr (R <= 24) {
     if (tma_ok) {
       using G = XGeom<R>;
