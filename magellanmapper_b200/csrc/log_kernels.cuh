@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(G * COLS / 2, 2)
 conv_march_kernel(const float* __restrict__ in0, const float* __restrict__ in1,
                   float* __restrict__ out0, float* __restrict__ out1, int n_axis,
                   int64_t inner, int64_t outer_stride, const __grid_constant__ LogWeights w,
-                  float scale) {
+                  float scale, int seg_len) {
   constexpr int PAIRS = COLS / 2;
   constexpr int THREADS = G * PAIRS;
   constexpr int STEP = NB * G;
@@ -295,8 +295,13 @@ conv_march_kernel(const float* __restrict__ in0, const float* __restrict__ in1,
   const int lch = (tid % CH) * 4;              // this thread's 16-byte column chunk
   const bool lact = lch < ncols;
 
+  // blockIdx.y splits the marched axis into segments of seg_len rows (a multiple of
+  // STEP) when the other two grid dimensions alone would leave SMs idle; a segment
+  // loads its own 2*RP halo rows.  Ring slots count rows from the segment's start.
+  const int a_base = blockIdx.y * seg_len;
+  const int a_end = min(n_axis, a_base + seg_len);
   // loader state: next row this thread copies, its ring slot, its global pointers
-  int la = -RP + tid / CH;
+  int la = a_base - RP + tid / CH;
   int lslot = tid / CH;
   const int64_t lstride = (int64_t)RPT * inner;
   const float* lg0 = in0 + base + lch + (int64_t)la * inner;   // dereferenced only when 0 <= la < n_axis
@@ -333,10 +338,10 @@ conv_march_kernel(const float* __restrict__ in0, const float* __restrict__ in1,
   };
 
   load_rows(STEP + 2 * RP);
-  const int nsteps = (n_axis + STEP - 1) / STEP;
+  const int nsteps = (a_end - a_base + STEP - 1) / STEP;
   const int grp = tid / PAIRS;
   const int col = (tid - grp * PAIRS) * 2;
-  int a_out = grp * NB;
+  int a_out = a_base + grp * NB;
   int cslot = grp * NB;                        // ring slot of input row a_out - RP
   float* o0 = out0 + base + col + (int64_t)a_out * inner;
   float* o1 = (MODE != MODE_LAST ? out1 : out0) + base + col + (int64_t)a_out * inner;
@@ -345,7 +350,7 @@ conv_march_kernel(const float* __restrict__ in0, const float* __restrict__ in1,
     __pipeline_wait_prior(0);
     __syncthreads();          // this step's rows have landed; step s-1's rows are free
     if (s + 1 < nsteps) load_rows(STEP);
-    if (a_out < n_axis && col < ncols) {
+    if (a_out < a_end && col < ncols) {
       float2 acc0[NB], acc1[NB];
 #pragma unroll
       for (int j = 0; j < NB; ++j) { acc0[j] = make_float2(0.f, 0.f); acc1[j] = make_float2(0.f, 0.f); }
@@ -359,7 +364,7 @@ conv_march_kernel(const float* __restrict__ in0, const float* __restrict__ in1,
         b1[i] = r1 + sl * COLS + col;
       }
       scatter_rows_ring<R, RP, MODE, NB, COLS, NBLK, 0>(b0, b1, acc0, acc1, w);
-      if (a_out + NB <= n_axis) {              // full block: no per-row bound checks
+      if (a_out + NB <= a_end) {               // full block: no per-row bound checks
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
           if (MODE == MODE_LAST) {
@@ -374,7 +379,7 @@ conv_march_kernel(const float* __restrict__ in0, const float* __restrict__ in1,
       } else {
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
-          if (a_out + j < n_axis) {
+          if (a_out + j < a_end) {
             if (MODE == MODE_LAST) {
               *reinterpret_cast<float2*>(o0) = make_float2(acc0[j].x * scale, acc0[j].y * scale);
             } else {

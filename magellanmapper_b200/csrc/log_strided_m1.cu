@@ -29,9 +29,22 @@ static int run(const float* in0, const float* in1, float* out0, float* out1, int
                                             (int)smem));
         configured = true;
       }
-      dim3 grid((unsigned)cdiv(inner, kCols), 1, (unsigned)outer);
+      // split the marched axis when columns x outer slices alone cannot fill the GPU
+      // (thin chunks, small ROIs): segments of a multiple of STEP rows, >= 4 steps each
+      constexpr int STEP = NBM * G;
+      const int64_t ctas = cdiv(inner, kCols) * outer;
+      const int64_t want = 2 * (int64_t)num_sms();
+      int nseg = 1;
+      if (ctas < want) {
+        nseg = (int)cdiv(want, ctas);
+        const int max_seg = (int)cdiv(n_axis, 4 * STEP);
+        if (nseg > max_seg) nseg = max_seg;
+        if (nseg < 1) nseg = 1;
+      }
+      const int seg_len = (int)cdiv(cdiv(n_axis, nseg), STEP) * STEP;
+      dim3 grid((unsigned)cdiv(inner, kCols), (unsigned)cdiv(n_axis, seg_len), (unsigned)outer);
       kern<<<grid, G * kCols / 2, smem, st>>>(in0, in1, out0, out1, n_axis, inner,
-                                              (int64_t)n_axis * inner, w, scale);
+                                              (int64_t)n_axis * inner, w, scale, seg_len);
       MMB_CHECK_LAUNCH();
       return MMB_OK;
     }
