@@ -343,7 +343,7 @@ def main():
             tt = torch.tensor([nb_e2e], device=device, dtype=torch.int64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             nb_e2e = int(tt.item())
-        d2h = nb_e2e * 20
+        d2h = nb_e2e * 8 * 8          # final table: 8 float64 columns per blob
         e2e = {"value": nvox * world * args.steps / t_e2e / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": int(nvox * 2) * world, "d2h_bytes_per_step": d2h}
         del host, host_np, img5d_host

@@ -98,12 +98,21 @@ class ChunkTables:
         return out[o]
 
 
+#: columns of the table ``detect_blobs_blocks`` returns (stack_detect.py:458-467):
+#: relative coordinates replaced by the seam-averaged absolute ones, abs columns dropped
+FINAL_COLS = ["z", "y", "x", "radius", "confirmed", "truth", "channel", "region"]
+
+
 def prune_merged(merged: torch.Tensor, overlap, tol, sub_roi_slices, sub_rois_offsets,
-                 channels: Sequence[int], overlap_padding=None):
+                 channels: Sequence[int], overlap_padding=None, final_layout: bool = False):
     """``StackPruner.prune_blobs_mp`` on a device-resident merged table.
 
     Returns ``((N', 11) float64 numpy table, DataFrame of pruning ratios)``; the
-    only device-to-host transfer of blob rows is the final table."""
+    only device-to-host transfer of blob rows is the final table.  With
+    ``final_layout`` the table is already what ``detect_blobs_blocks`` makes of it
+    afterwards (``Blobs.replace_rel_with_abs_blob_coords`` then
+    ``remove_abs_blob_coords(True)``): ``(N', 8)`` in ``FINAL_COLS`` order, built on
+    the device so that the host never copies the wide table."""
     from .. import gpu
     if merged is None or merged.shape[0] == 0:
         return None, None
@@ -174,6 +183,13 @@ def prune_merged(merged: torch.Tensor, overlap, tol, sub_roi_slices, sub_rois_of
             cur = torch.cat(keep_parts + seam_parts)
         order.append(cur)
     order = order[0] if len(order) == 1 else torch.cat(order)
+    if final_layout:
+        out = torch.empty((order.shape[0], len(FINAL_COLS)), dtype=torch.float64,
+                          device=merged.device)
+        out[:, 0:3] = abs_zyx[order]
+        out[:, 3:7] = merged[order, 3:7]
+        out[:, 7] = merged[order, 10]
+        return out.cpu().numpy(), pd.DataFrame(ratios_out)
     out = merged[order, :N_COLS]
     out[:, 7:10] = abs_zyx[order]
     return out.cpu().numpy(), pd.DataFrame(ratios_out)

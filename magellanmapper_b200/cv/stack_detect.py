@@ -465,6 +465,7 @@ def detect_blobs_blocks(filename_base: str, img5d: np_io.Image5d,
         coloc = False
 
     t_det = time()
+    final_on_device = False
     if channels is None:
         _, channels = plot_3d.setup_channels(roi, channels, 3)
     settings = config.get_roi_profile(channels[0])
@@ -479,7 +480,8 @@ def detect_blobs_blocks(filename_base: str, img5d: np_io.Image5d,
         t_prune = time()
         segments_all, df_pruning = device_tables.prune_merged(
             merged, blocks.overlap, blocks.tol, blocks.sub_roi_slices,
-            blocks.sub_rois_offsets, channels, blocks.overlap_padding)
+            blocks.sub_rois_offsets, channels, blocks.overlap_padding, final_layout=True)
+        final_on_device = True
         pruning_time = time() - t_prune
     else:
         seg_rois = StackDetector.detect_blobs_sub_rois(
@@ -500,8 +502,14 @@ def detect_blobs_blocks(filename_base: str, img5d: np_io.Image5d,
                      for c in df_pruning.columns[1:]}
             pd.DataFrame(means).to_csv("blob_ratios_means.csv", index=False)
 
-    blobs = detector.Blobs(segments_all, path=filename_blobs)
-    if segments_all is not None:
+    if final_on_device:
+        # the device route already delivered the final layout
+        from . import device_tables
+        blobs = detector.Blobs(segments_all, path=filename_blobs,
+                               cols=list(device_tables.FINAL_COLS))
+    else:
+        blobs = detector.Blobs(segments_all, path=filename_blobs)
+    if segments_all is not None and not final_on_device:
         # the abs columns carried the seam-averaged positions; they become the
         # coordinates and the helper columns go away (stack_detect.py:458-467)
         blobs.replace_rel_with_abs_blob_coords(segments_all)

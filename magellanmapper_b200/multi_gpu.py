@@ -315,6 +315,7 @@ def detect_blobs_blocks_slabs(filename_base: str, slab, held: Sequence[Range],
     rows, z_bounds, wanted = chunk_row_plan(shape, blocks, held)
     ext = exchange_planes(slab, held, wanted, group)
     w0 = wanted[rank][0]
+    final_on_device = False
 
     grid = blocks.sub_roi_slices.shape
     local_slices = np.empty(grid, dtype=object)
@@ -344,7 +345,8 @@ def detect_blobs_blocks_slabs(filename_base: str, slab, held: Sequence[Range],
         # runs of chunk rows are contiguous and in rank order = chunk-grid order
         segments_all, df_pruning = device_tables.prune_merged(
             torch.cat(parts), blocks.overlap, blocks.tol, blocks.sub_roi_slices,
-            blocks.sub_rois_offsets, channels, blocks.overlap_padding)
+            blocks.sub_rois_offsets, channels, blocks.overlap_padding, final_layout=True)
+        final_on_device = True
     else:
         seg_rois = None
         if coords:
@@ -361,8 +363,12 @@ def detect_blobs_blocks_slabs(filename_base: str, slab, held: Sequence[Range],
             None, seg_all, blocks.overlap, blocks.tol, blocks.sub_roi_slices,
             blocks.sub_rois_offsets, channels, blocks.overlap_padding)
     filename_blobs = libmag.combine_paths(filename_base, config.SUFFIX_BLOBS)
-    blobs = detector.Blobs(segments_all, path=filename_blobs)
-    if segments_all is not None:
+    if final_on_device:
+        from .cv import device_tables as _dt
+        blobs = detector.Blobs(segments_all, path=filename_blobs, cols=list(_dt.FINAL_COLS))
+    else:
+        blobs = detector.Blobs(segments_all, path=filename_blobs)
+    if segments_all is not None and not final_on_device:
         blobs.replace_rel_with_abs_blob_coords(segments_all)
         blobs.blobs = segments_all
         segments_all = blobs.remove_abs_blob_coords(True)
