@@ -320,9 +320,8 @@ def main():
                 _, _, b = stack_detect.detect_blobs_stack(os.path.join(tmp, f"e2e_r{rank}"),
                                                           img5d_host)
             else:
-                slab = host.to(device, non_blocking=True)
                 _, _, b = multi_gpu.detect_blobs_blocks_slabs(
-                    os.path.join(tmp, f"e2e_r{rank}"), slab, held, gshape, [0])
+                    os.path.join(tmp, f"e2e_r{rank}"), host_np, held, gshape, [0])
                 if b is not None:
                     b.save_archive()
             return b

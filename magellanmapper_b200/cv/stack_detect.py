@@ -185,12 +185,16 @@ class StackDetector(object):
 
     @classmethod
     def detect_blobs_sub_rois_device(cls, img, sub_roi_slices, sub_rois_offsets,
-                                     denoise_max_shape, channel, coords=None):
+                                     denoise_max_shape, channel, coords=None,
+                                     prefix=None, suffix=None):
         """``detect_blobs_sub_rois`` with the per-chunk tables left on the device:
         returns the merged (N, 14) float64 CUDA tensor of
         ``device_tables.ChunkTables.merged`` (None when nothing was found) instead
         of an object array of host tables.  No ``exclude_border`` support (the
-        caller falls back to the host route for that)."""
+        caller falls back to the host route for that).  ``prefix`` / ``suffix``
+        (device tensors of whole planes around a HOST ``img``, see
+        ``gpu.StripFeeder``) let ``multi_gpu`` stream a rank's own planes from host
+        memory while the halo planes of its neighbours are already in HBM."""
         from collections import deque
         from .. import gpu
         from . import device_tables
@@ -208,9 +212,11 @@ class StackDetector(object):
             for j in cols:
                 sy = sub_roi_slices[todo[0][0], j, todo[0][2]][1]
                 y_ranges.append((sy.start, sy.stop))
-            feeder = gpu.StripFeeder(img, y_ranges)
+            feeder = gpu.StripFeeder(img, y_ranges, prefix=prefix, suffix=suffix)
             todo.sort(key=lambda c: (c[1], c[0], c[2]))
         else:
+            if prefix is not None or suffix is not None:
+                raise ValueError("prefix/suffix planes need a C-contiguous host image")
             img = gpu.upload_if_fits(img)
         largest = [max(s[a].stop - s[a].start for s in sub_roi_slices.flat) for a in range(3)]
         det = cls._workspace(tuple(largest))

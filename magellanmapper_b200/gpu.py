@@ -121,7 +121,11 @@ class StripFeeder:
     column).  Each strip is one pitched DMA (``mmb_upload_pieces``: one contiguous
     piece per z-plane) on a copy stream into one of two device buffers."""
 
-    def __init__(self, img: np.ndarray, y_ranges: Sequence[Tuple[int, int]], device=None):
+    def __init__(self, img: np.ndarray, y_ranges: Sequence[Tuple[int, int]], device=None,
+                 prefix: Optional[torch.Tensor] = None, suffix: Optional[torch.Tensor] = None):
+        """``prefix`` / ``suffix``: device tensors of whole planes that precede /
+        follow ``img`` along z (halo planes received from a neighbouring rank);
+        every strip is then ``[prefix; img; suffix][:, y0:y1]``."""
         if not (isinstance(img, np.ndarray) and img.flags.c_contiguous and img.ndim in (3, 4)
                 and img.dtype in _NP2MMB):
             raise TypeError("StripFeeder needs a C-contiguous (z,y,x[,c]) array of a supported dtype")
@@ -132,9 +136,17 @@ class StripFeeder:
         self.tdtype = torch.int16 if img.dtype == np.uint16 else torch.from_numpy(
             np.zeros(1, img.dtype)).dtype
         rows = max(b - a for a, b in self.ranges)
-        self.bufs = [torch.empty((img.shape[0], rows) + tuple(img.shape[2:]), dtype=self.tdtype,
+        self.prefix = prefix if prefix is not None and prefix.shape[0] else None
+        self.suffix = suffix if suffix is not None and suffix.shape[0] else None
+        self.n_pre = 0 if self.prefix is None else int(self.prefix.shape[0])
+        self.n_suf = 0 if self.suffix is None else int(self.suffix.shape[0])
+        self.planes = self.n_pre + int(img.shape[0]) + self.n_suf
+        self.bufs = [torch.empty((self.planes, rows) + tuple(img.shape[2:]), dtype=self.tdtype,
                                  device=self.device) for _ in range(min(2, len(self.ranges)))]
         self.copy_stream = torch.cuda.Stream(device=self.device)
+        # halo planes are produced on the caller's stream (NCCL recv): order the copy
+        # stream after them
+        self.copy_stream.wait_stream(torch.cuda.current_stream())
         self.uploaded = [None] * len(self.ranges)      # events on the copy stream
         self.released = [None] * len(self.ranges)      # events on the compute stream
         for j in range(len(self.bufs)):                # both buffers are free: fill them
@@ -149,23 +161,37 @@ class StripFeeder:
             if j >= len(self.bufs) and self.released[j - len(self.bufs)] is not None:
                 self.copy_stream.wait_event(self.released[j - len(self.bufs)])
             src = img.ctypes.data + y0 * row_bytes
-            _lib.check(self.lib.mmb_upload_pieces(
-                C.c_void_p(buf.data_ptr()), C.c_void_p(src), int(img.shape[0]),
-                (y1 - y0) * row_bytes, int(img.shape[1]) * row_bytes,
-                C.c_void_p(self.copy_stream.cuda_stream)))
+            piece = (y1 - y0) * row_bytes
+            view = self._view(buf, y0, y1)
+            if img.shape[0]:
+                _lib.check(self.lib.mmb_upload_pieces(
+                    C.c_void_p(view[self.n_pre:].data_ptr()), C.c_void_p(src), int(img.shape[0]),
+                    piece, int(img.shape[1]) * row_bytes,
+                    C.c_void_p(self.copy_stream.cuda_stream)))
+            if self.prefix is not None:
+                view[:self.n_pre].copy_(self.prefix[:, y0:y1].view(self.tdtype)
+                                        if self.prefix.dtype != self.tdtype
+                                        else self.prefix[:, y0:y1], non_blocking=True)
+            if self.suffix is not None:
+                view[self.n_pre + img.shape[0]:].copy_(
+                    self.suffix[:, y0:y1].view(self.tdtype) if self.suffix.dtype != self.tdtype
+                    else self.suffix[:, y0:y1], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
         self.uploaded[j] = ev
+
+    def _view(self, buf: torch.Tensor, y0: int, y1: int) -> torch.Tensor:
+        # dense strip: the buffer is viewed with this strip's own row count
+        inner = tuple(self.img.shape[2:])
+        n = self.planes * (y1 - y0) * int(np.prod(inner))
+        return buf.view(-1)[:n].view((self.planes, y1 - y0) + inner)
 
     def strip(self, j: int) -> torch.Tensor:
         """Device view of strip ``j`` (shape ``(Z, y1 - y0, X[, C])``); the current
         stream waits for its upload, and the upload of strip ``j + 1`` is started."""
         torch.cuda.current_stream().wait_event(self.uploaded[j])
         y0, y1 = self.ranges[j]
-        buf = self.bufs[j % len(self.bufs)]
-        # dense upload: the buffer is viewed with this strip's own row count
-        n = self.img.shape[0] * (y1 - y0) * int(np.prod(self.img.shape[2:]))
-        return buf.view(-1)[:n].view((self.img.shape[0], y1 - y0) + tuple(self.img.shape[2:]))
+        return self._view(self.bufs[j % len(self.bufs)], y0, y1)
 
     def release(self, j: int) -> None:
         """Every kernel reading strip ``j`` has been enqueued on the current stream."""

@@ -179,6 +179,50 @@ def exchange_planes(local: torch.Tensor, held: Sequence[Range], wanted: Sequence
     return ext
 
 
+def exchange_edges(host_slab: np.ndarray, held: Sequence[Range], wanted: Sequence[Range],
+                   group=None, device=None):
+    """Halo exchange for a slab that still lives in HOST memory: only the planes other
+    ranks want are uploaded and sent; returns ``(prefix, own, suffix)`` where
+    ``prefix`` / ``suffix`` are device tensors with the wanted planes below / above
+    this rank's slab and ``own`` is the host view of the wanted part of the slab
+    itself (to be streamed by ``gpu.StripFeeder``)."""
+    rank, world = _world(group)
+    dev = device or torch.device("cuda", torch.cuda.current_device())
+    h0, h1 = held[rank]
+    w0, w1 = wanted[rank]
+    if host_slab.shape[0] != h1 - h0:
+        raise ValueError(f"rank {rank} holds {host_slab.shape[0]} planes, expected {h1 - h0}")
+    as_t = (lambda a: torch.from_numpy(a.view(np.int16) if a.dtype == np.uint16 else a))
+    tail = tuple(host_slab.shape[1:])
+    tdtype = as_t(host_slab[:0]).dtype
+    n_pre = max(0, min(w1, h0) - w0)
+    n_suf = max(0, w1 - max(w0, h1))
+    prefix = torch.empty((n_pre,) + tail, dtype=tdtype, device=dev)
+    suffix = torch.empty((n_suf,) + tail, dtype=tdtype, device=dev)
+    a, b = max(w0, h0), min(w1, h1)
+    own = host_slab[max(0, a - h0):max(0, b - h0)] if a < b else host_slab[:0]
+    if world > 1:
+        ops, keep = [], []
+        g = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+        for src, dst, z0, z1 in transfer_plan(held, wanted):
+            if src == rank:
+                buf = as_t(np.ascontiguousarray(host_slab[z0 - h0:z1 - h0])).to(dev).view(torch.uint8)
+                keep.append(buf)
+                ops.append(dist.P2POp(dist.isend, buf, g(dst), group))
+            elif dst == rank:
+                if z1 <= h0:
+                    view = prefix[z0 - w0:z1 - w0]
+                else:
+                    view = suffix[z0 - max(w0, h1):z1 - max(w0, h1)]
+                ops.append(dist.P2POp(dist.irecv, view.view(torch.uint8), g(src), group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+    elif n_pre or n_suf:
+        raise ValueError(f"planes {wanted[rank]} are not all held ({held[rank]})")
+    return prefix, own, suffix
+
+
 def gather_rows(rows: Optional[np.ndarray], n_cols: int, group=None, dst: int = 0,
                 dtype=np.float64) -> Optional[List[np.ndarray]]:
     """Variable-length gather of ``(n_r, n_cols)`` tables to ``dst``: row counts
@@ -294,8 +338,10 @@ def detect_blobs_blocks_slabs(filename_base: str, slab, held: Sequence[Range],
     """``stack_detect.detect_blobs_blocks`` over a volume sharded as z-slabs.
 
     Args:
-        slab: this rank's planes ``held[rank]`` of the (z, y, x[, c]) volume,
-            a CUDA tensor (uint16 as int16 bits is accepted like everywhere).
+        slab: this rank's planes ``held[rank]`` of the (z, y, x[, c]) volume: a
+            CUDA tensor (uint16 as int16 bits is accepted like everywhere), or a
+            C-contiguous HOST array, which is then streamed to the device strip by
+            strip under the kernels (only neighbours' halo planes move up front).
         held: the slab [z0, z1) of every rank, in rank order.
         global_shape: (Z, Y, X) of the whole volume.
 
@@ -313,7 +359,19 @@ def detect_blobs_blocks_slabs(filename_base: str, slab, held: Sequence[Range],
     shape = tuple(int(v) for v in global_shape[:3]) + tuple(slab.shape[3:])
     blocks = stack_detect.setup_blocks(settings, shape)
     rows, z_bounds, wanted = chunk_row_plan(shape, blocks, held)
-    ext = exchange_planes(slab, held, wanted, group)
+    host_slab = isinstance(slab, np.ndarray)
+    streamed = (host_slab and slab.flags.c_contiguous and blocks.exclude_border is None
+                and stack_detect.DEVICE_TABLES)
+    prefix = suffix = None
+    if streamed:
+        # the slab stays on the host and is streamed strip by strip under the kernels;
+        # only the halo planes of the neighbours are exchanged up front
+        prefix, ext, suffix = exchange_edges(slab, held, wanted, group)
+    else:
+        if host_slab:
+            slab = torch.from_numpy(np.ascontiguousarray(
+                slab.view(np.int16) if slab.dtype == np.uint16 else slab)).cuda()
+        ext = exchange_planes(slab, held, wanted, group)
     w0 = wanted[rank][0]
     final_on_device = False
 
@@ -338,8 +396,10 @@ def detect_blobs_blocks_slabs(filename_base: str, slab, held: Sequence[Range],
         if coords:
             merged = stack_detect.StackDetector.detect_blobs_sub_rois_device(
                 ext, local_slices, blocks.sub_rois_offsets, blocks.denoise_max_shape,
-                channels, coords=coords)
-        parts = gather_tensor_rows(merged, device_tables.N_MERGED, group, device=slab.device)
+                channels, coords=coords, prefix=prefix, suffix=suffix)
+        parts = gather_tensor_rows(
+            merged, device_tables.N_MERGED, group,
+            device=torch.device("cuda", torch.cuda.current_device()) if host_slab else slab.device)
         if rank != 0:
             return None, None, None
         # runs of chunk rows are contiguous and in rank order = chunk-grid order

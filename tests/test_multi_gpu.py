@@ -115,6 +115,14 @@ def _gloo_worker(rank, world, port, out_dir):
         wanted2 = [(0, 40), (20, 20)]
         ext2 = mg.exchange_planes(vol[held[rank][0]:held[rank][1]].clone(), held, wanted2)
         assert torch.equal(ext2, vol[wanted2[rank][0]:wanted2[rank][1]])
+        # host-resident slab: only the halo planes are exchanged
+        host = vol.numpy().view(np.uint16)
+        pre, own, suf = mg.exchange_edges(host[held[rank][0]:held[rank][1]], held, wanted,
+                                          device=torch.device("cpu"))
+        w0, w1 = wanted[rank]
+        whole = np.concatenate([pre.numpy().view(np.uint16), own, suf.numpy().view(np.uint16)])
+        np.testing.assert_array_equal(whole, host[w0:w1])
+        assert own.base is not None and len(own) == min(w1, held[rank][1]) - max(w0, held[rank][0])
         # variable-length gathers (float64 tables and int32 candidate records)
         mine = np.full((3 + 2 * rank, 14), float(rank)) + np.arange(14)
         parts = mg.gather_rows(mine if rank == 0 else mine, 14)
@@ -152,6 +160,10 @@ def test_slab_driver_world1_equals_reference_vectors(golden_dir, tmp_path):
     vol = torch.from_numpy(g["vol"].view(np.int16)).cuda()
     _, _, blobs = mg.detect_blobs_blocks_slabs(config.filename, vol, [(0, vol.shape[0])],
                                                vol.shape)
+    np.testing.assert_array_equal(blobs.blobs, g["plain_blobs"])
+    # host slab: streamed through gpu.StripFeeder
+    _, _, blobs = mg.detect_blobs_blocks_slabs(config.filename, np.ascontiguousarray(g["vol"]),
+                                               [(0, vol.shape[0])], vol.shape)
     np.testing.assert_array_equal(blobs.blobs, g["plain_blobs"])
     stack_detect.StackDetector.release_workspace()
 
@@ -244,10 +256,15 @@ def _nccl_worker(rank, world, port, out_dir, golden_dir):
         slab = vol[held[rank][0]:held[rank][1]].cuda()
         _, _, blobs = mg.detect_blobs_blocks_slabs(os.path.join(out_dir, "nccl"), slab, held,
                                                    vol.shape)
+        # the same from a HOST slab (streamed strip by strip, halo planes exchanged first)
+        host_slab = np.ascontiguousarray(g["vol"][held[rank][0]:held[rank][1]])
+        _, _, blobs_h = mg.detect_blobs_blocks_slabs(os.path.join(out_dir, "nccl_h"), host_slab,
+                                                     held, vol.shape)
         if rank == 0:
             np.testing.assert_array_equal(blobs.blobs, g["plain_blobs"])
+            np.testing.assert_array_equal(blobs_h.blobs, g["plain_blobs"])
         else:
-            assert blobs is None
+            assert blobs is None and blobs_h is None
         open(os.path.join(out_dir, f"ok{rank}"), "w").close()
     finally:
         dist.destroy_process_group()
