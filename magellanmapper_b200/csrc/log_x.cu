@@ -196,6 +196,230 @@ conv_x_tma_kernel(const __grid_constant__ CUtensorMap tm_in,
   if (tid == 0) tma_wait_read<0>();
 }
 
+// ---- warp-specialised x sweep ------------------------------------------------------
+// conv_x_ws_kernel: one persistent CTA per SM, three roles that only meet at mbarriers:
+//   warp 0          producer: TMA loads of the input window into a kWsIn-deep ring
+//   warps 1..NCW    consumers: lane = row, warp = 16-output segment; copy the window to
+//                   registers (which frees the ring slot), FFMA2 scatter, write the
+//                   (A, B) results into one of kWsOut staging buffers
+//   warp NCW+1      store issuer: TMA stores of a full staging buffer, frees it when the
+//                   stores have read it
+// Nothing is CTA-wide, so loads, arithmetic and stores of different tiles overlap inside
+// one SM.  (The CTA-synchronous kernel above adds its arithmetic to a 0.33 ms
+// load/window/store skeleton instead of hiding it: 0.39 / 0.46 / 0.56 ms at r = 12 / 16 /
+// 20 on a 505^3 chunk; this one: 0.37 / 0.43 / 0.49 ms with 16 consumer warps, and it
+// keeps improving with the consumer count - 8: 0.62, 12: 0.43 at r = 16 - until shared
+// memory for the staging buffers runs out.  Writing results straight from registers,
+// 64 bytes per lane, frees that memory but costs more than it buys: 0.68 ms.)  'reflect'
+// at the x faces is applied by the consumers while they fill their register window.
+#ifndef MMB_WS_IN
+#define MMB_WS_IN 2
+#endif
+#ifndef MMB_WS_OUT
+#define MMB_WS_OUT 2
+#endif
+#ifndef MMB_WS_NCW
+#define MMB_WS_NCW 16
+#endif
+constexpr int kWsIn = MMB_WS_IN;          // input ring depth
+constexpr int kWsOut = MMB_WS_OUT;         // output staging buffers
+constexpr int kWsNCW = MMB_WS_NCW;         // consumer warps = 16-column segments per tile
+constexpr int kWsCols = 16 * kWsNCW;
+constexpr int kWsThreads = 32 * (kWsNCW + 2);
+constexpr int kWsOutBoxes = (kWsCols + 31) / 32;
+
+template <int R>
+struct WsGeom {
+  static constexpr int R4 = (R + 3) / 4 * 4;
+  static constexpr int WIN = kWsCols + 2 * R4;
+  static constexpr int NBOX = (WIN + 31) / 32;
+  static constexpr int W = 16 + 2 * R4;                // per-thread window, floats
+  static constexpr int STAGE_BYTES = NBOX * kBoxBytes;
+  static constexpr int OUT_BYTES = 2 * kWsOutBoxes * kBoxBytes;     // A boxes then B boxes
+#ifdef MMB_WS_DIRECT
+  static constexpr size_t SMEM = (size_t)kWsIn * STAGE_BYTES + 1024 + 256;
+#else
+  static constexpr size_t SMEM = (size_t)kWsIn * STAGE_BYTES + kWsOut * OUT_BYTES + 1024 + 256;
+#endif
+};
+
+template <int R>
+__global__ void __launch_bounds__(kWsThreads, 1)
+conv_x_ws_kernel(const __grid_constant__ CUtensorMap tm_in,
+                 const __grid_constant__ CUtensorMap tm_a,
+                 const __grid_constant__ CUtensorMap tm_b, int64_t nrows, int X, int n_xt,
+                 int n_tiles, const __grid_constant__ LogWeights w, float* __restrict__ outA,
+                 float* __restrict__ outB, int64_t pitch) {
+  using G = WsGeom<R>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* s_in = base;
+  unsigned char* s_out = base + kWsIn * G::STAGE_BYTES;
+#ifdef MMB_WS_DIRECT
+  uint64_t* full_in = reinterpret_cast<uint64_t*>(s_out);
+#else
+  uint64_t* full_in = reinterpret_cast<uint64_t*>(s_out + kWsOut * G::OUT_BYTES);
+#endif
+  uint64_t* empty_in = full_in + kWsIn;
+  uint64_t* full_out = empty_in + kWsIn;
+  uint64_t* empty_out = full_out + kWsOut;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < kWsIn; ++s) { mbar_init(&full_in[s], 1); mbar_init(&empty_in[s], kWsNCW); }
+    for (int o = 0; o < kWsOut; ++o) { mbar_init(&full_out[o], kWsNCW); mbar_init(&empty_out[o], 1); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    // ---- producer ----------------------------------------------------------------
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const int s = it % kWsIn;
+        if (it >= kWsIn) mbar_wait(&empty_in[s], (uint32_t)((it / kWsIn) - 1) & 1u);
+        const int rt = t / n_xt, xt = t - rt * n_xt;
+        mbar_arrive_expect_tx(&full_in[s], G::STAGE_BYTES);
+#pragma unroll
+        for (int b = 0; b < G::NBOX; ++b)
+          tma_load_2d(s_in + s * G::STAGE_BYTES + b * kBoxBytes, &tm_in, &full_in[s],
+                      xt * kWsCols - G::R4 + 32 * b, rt * kXRows);
+      }
+    }
+  } else if (warp <= kWsNCW) {
+    // ---- consumers ---------------------------------------------------------------
+    const int seg = warp - 1;
+    const int key = (lane & 7) << 4;
+    int it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int s = it % kWsIn;
+      const int rt = t / n_xt, xt = t - rt * n_xt;
+      const int x0 = xt * kWsCols;
+      const int xs = x0 - G::R4 + 16 * seg;            // global x of this thread's win[0]
+      const unsigned char* st_in = s_in + s * G::STAGE_BYTES;
+      mbar_wait(&full_in[s], (uint32_t)(it / kWsIn) & 1u);
+      float win[G::W];
+      const unsigned char* rowp = st_in + lane * 128;
+#pragma unroll
+      for (int c = 0; c < G::W / 4; ++c) {
+        const int ci = seg * 4 + c;
+        const float4 v = *reinterpret_cast<const float4*>(rowp + (ci >> 3) * kBoxBytes +
+                                                          (((ci & 7) << 4) ^ key));
+        win[4 * c + 0] = v.x; win[4 * c + 1] = v.y; win[4 * c + 2] = v.z; win[4 * c + 3] = v.w;
+      }
+      // scipy 'reflect' at the x faces (TMA zero-filled those positions); both tests are
+      // warp-uniform and false for interior windows.  Left face: only the window that
+      // starts at x = -R4, mirrored inside the registers.  Right face: the mirrored
+      // sample x' = 2X - 1 - x is read back from the tile (the host checks X >= WIN, so
+      // it is always inside it).
+      if (xs == -G::R4) {
+#pragma unroll
+        for (int i = 0; i < G::R4; ++i) win[i] = win[2 * G::R4 - 1 - i];
+      }
+      if (G::R4 > 16 && xs == 16 - G::R4) {            // the second segment also starts left of 0
+#pragma unroll
+        for (int i = 0; i < G::R4 - 16; ++i) win[i] = win[2 * (G::R4 - 16) - 1 - i];
+      }
+      if (xs + G::W > X) {
+#pragma unroll
+        for (int i = 0; i < G::W; ++i) {
+          const int x = xs + i;
+          if (x >= X) {
+            const int p = 2 * X - 1 - x - (x0 - G::R4);
+            float v = 0.f;
+            if (p >= 0 && p < G::WIN)
+              v = *reinterpret_cast<const float*>(st_in + x_sw_off(lane, p));
+            win[i] = v;
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_in[s]);         // the slot may be refilled
+
+      float2 acc[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int i = G::R4 - R; i < G::R4 + 16 + R; ++i) {
+        const float2 vv = make_float2(win[i], win[i]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int tt = i - (G::R4 + j);
+          if (tt >= -R && tt <= R) acc[j] = ffma2(vv, w.gh[tt < 0 ? -tt : tt], acc[j]);
+        }
+      }
+
+#ifdef MMB_WS_DIRECT
+      {
+        // results leave straight from the registers: a lane owns 64 contiguous bytes of
+        // its row in A and in B (no staging buffer, no store warp)
+        const int64_t row = (int64_t)rt * kXRows + lane;
+        const int xo = x0 + 16 * seg;
+        if (row < nrows) {
+          float* pa = outA + row * pitch + xo;
+          float* pb = outB + row * pitch + xo;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (xo + 4 * q < (int)pitch) {
+              *reinterpret_cast<float4*>(pa + 4 * q) = make_float4(
+                  acc[4 * q].x, acc[4 * q + 1].x, acc[4 * q + 2].x, acc[4 * q + 3].x);
+              *reinterpret_cast<float4*>(pb + 4 * q) = make_float4(
+                  acc[4 * q].y, acc[4 * q + 1].y, acc[4 * q + 2].y, acc[4 * q + 3].y);
+            }
+          }
+        }
+        continue;
+      }
+#endif
+      const int o = it % kWsOut;
+      if (it >= kWsOut) mbar_wait(&empty_out[o], (uint32_t)((it / kWsOut) - 1) & 1u);
+      unsigned char* oa = s_out + o * G::OUT_BYTES + lane * 128;
+      unsigned char* ob = oa + kWsOutBoxes * kBoxBytes;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int co = seg * 4 + q;
+        const int off = (co >> 3) * kBoxBytes + (((co & 7) << 4) ^ key);
+        *reinterpret_cast<float4*>(oa + off) =
+            make_float4(acc[4 * q].x, acc[4 * q + 1].x, acc[4 * q + 2].x, acc[4 * q + 3].x);
+        *reinterpret_cast<float4*>(ob + off) =
+            make_float4(acc[4 * q].y, acc[4 * q + 1].y, acc[4 * q + 2].y, acc[4 * q + 3].y);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_out[o]);
+    }
+  } else {
+    // ---- store issuer --------------------------------------------------------------
+#ifdef MMB_WS_DIRECT
+    return;
+#endif
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const int o = it % kWsOut;
+        const int rt = t / n_xt, xt = t - rt * n_xt;
+        const int x0 = xt * kWsCols;
+        mbar_wait(&full_out[o], (uint32_t)(it / kWsOut) & 1u);
+        const unsigned char* oa = s_out + o * G::OUT_BYTES;
+        const unsigned char* ob = oa + kWsOutBoxes * kBoxBytes;
+#pragma unroll
+        for (int b = 0; b < kWsOutBoxes; ++b) {
+          if (x0 + 32 * b < X) {
+            tma_store_2d(&tm_a, oa + b * kBoxBytes, x0 + 32 * b, rt * kXRows);
+            tma_store_2d(&tm_b, ob + b * kBoxBytes, x0 + 32 * b, rt * kXRows);
+          }
+        }
+        tma_commit();
+        tma_wait_read<0>();
+        mbar_arrive(&empty_out[o]);
+      }
+    }
+  }
+}
+
 #ifdef MMB_X_WARP_KERNEL
 // ---- warp-autonomous x sweep (experimental, not the default) -------------------------
 // Measured on B200, 505^3, r = 12/16/20: 0.47/0.49/0.61 ms single-stage (17 warps/SM),
@@ -387,6 +611,38 @@ static int run_x(const float* in, float* outA, float* outB, int64_t nrows, int X
       while (full > 1 && gcd(full * kWWarps, n_xt) != 1) --full;
       kern<<<(unsigned)(want < full ? want : full), 32 * kWWarps, G::SMEM, st>>>(
           in, outA, outB, nrows, X, pitch, n_xt, (int)n_tiles64, w);
+      MMB_CHECK_LAUNCH();
+      return MMB_OK;
+    }
+  }
+#endif
+#ifndef MMB_X_NO_WS
+  if constexpr (R <= 24) {
+    using G = WsGeom<R>;
+    const int n_xt = (int)cdiv(X, kWsCols);
+    const int64_t n_tiles64 = cdiv(nrows, kXRows) * n_xt;
+    // long launches only: with a few tiles per SM the pipeline never fills and the
+    // CTA-synchronous kernel below (two CTAs per SM, smaller tiles) is faster
+    if (tma_ok && X >= G::WIN && n_tiles64 >= 16 * (int64_t)num_sms() &&
+        n_tiles64 < ((int64_t)1 << 31)) {
+      auto kern = conv_x_ws_kernel<R>;
+      static bool configured = false;
+      if (!configured) {
+        MMB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)G::SMEM));
+        configured = true;
+      }
+      CUtensorMap tin, ta, tb;
+      const uint64_t dims[2] = {(uint64_t)X, (uint64_t)nrows};
+      const uint64_t strides[1] = {(uint64_t)pitch * sizeof(float)};
+      const uint32_t box[2] = {32, 32};
+      if (encode_tensor_map_f32(&tin, in, 2, dims, strides, box, true) ||
+          encode_tensor_map_f32(&ta, outA, 2, dims, strides, box, true) ||
+          encode_tensor_map_f32(&tb, outB, 2, dims, strides, box, true))
+        return MMB_ERR_CUDA;
+      const int64_t grid = n_tiles64 < num_sms() ? n_tiles64 : num_sms();
+      kern<<<(unsigned)grid, kWsThreads, G::SMEM, st>>>(tin, ta, tb, nrows, X, n_xt,
+                                                        (int)n_tiles64, w, outA, outB, pitch);
       MMB_CHECK_LAUNCH();
       return MMB_OK;
     }

@@ -78,7 +78,8 @@ def test_to_float_channel_last(gpu):
 
 # ------------------------------------------------------------ single sweeps
 
-@pytest.mark.parametrize("shape", [(40, 70, 90), (12, 48, 505), (3, 5, 7), (50, 130, 64)])
+@pytest.mark.parametrize("shape", [(40, 70, 90), (12, 48, 505), (3, 5, 7), (50, 130, 64),
+                                   (24, 37, 300), (20, 33, 777), (70, 300, 330)])
 @pytest.mark.parametrize("sigma", [1.0, 3.0, 3.6666666666666665, 5.0, 8.0])
 def test_log_pass_each_axis(gpu, shape, sigma):
     rng = np.random.default_rng(int(sigma * 10) + shape[0])
@@ -104,6 +105,22 @@ def test_log_pass_each_axis(gpu, shape, sigma):
         o0, _ = gpu.log_pass(da, db, X, axis, 2, sigma, scale=-sigma * sigma)
         torch.cuda.synchronize()
         assert _rel_err(o0[:, :, :X].cpu().numpy(), -sigma * sigma * (ha + gb)) < REL_TOL
+
+
+@pytest.mark.parametrize("sigma", [3.0, 4.111111111111111, 5.0])
+def test_x_sweep_long_launch(gpu, sigma):
+    """Launches with >= 16 tiles per SM take the warp-specialised x sweep
+    (conv_x_ws_kernel: TMA producer warp, 16 consumer warps, store warp); both x
+    faces, a nearly empty last tile (X = 520 = 2 * 256 + 8) and a row tail."""
+    shape = (61, 630, 520)
+    rng = np.random.default_rng(int(sigma * 7))
+    a = rng.uniform(0, 1, shape).astype(np.float32).astype(np.float64)
+    g, h, r = _kernels(sigma)
+    da = _vol_to_dev(gpu, a)
+    o0, o1 = gpu.log_pass(da, None, shape[2], 2, 0, sigma)
+    torch.cuda.synchronize()
+    assert _rel_err(o0[:, :, :shape[2]].cpu().numpy(), ndi.correlate1d(a, g, 2, mode="reflect")) < REL_TOL
+    assert _rel_err(o1[:, :, :shape[2]].cpu().numpy(), ndi.correlate1d(a, h, 2, mode="reflect")) < REL_TOL
 
 
 def test_log_pass_large_radius_fallback(gpu):
