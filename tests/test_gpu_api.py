@@ -209,3 +209,32 @@ def test_strip_feeder_delivers_every_strip():
             feeder.release(j)
     with pytest.raises(TypeError):
         gpu.StripFeeder(np.asfortranarray(np.zeros((4, 5, 6), np.uint16)), [(0, 5)])
+
+
+def test_config2_full_size_resident_equals_streamed(tmp_path):
+    """BASELINE config 2 at full size (512x2048x2048 uint16, 50 chunks): the stack
+    resident in HBM and the same stack streamed from host memory strip by strip
+    (different chunk order, different buffers) give the same table bit for bit; every
+    blob lies inside the volume, on integer coordinates, with a radius of the ladder."""
+    import bench
+    dev = torch.device("cuda", 0)
+    shape = (512, 2048, 2048)
+    vol = bench.make_device_volume(shape, 1, dev)
+    nm = bench.near_max_device(vol)
+    bench.setup_config(nm, str(tmp_path / "c2"))
+    os.chdir(tmp_path)
+    _, _, res = stack_detect.detect_blobs_blocks(
+        str(tmp_path / "c2"), np_io.Image5d(vol[None]), None, None, [0], False, False, True)
+    host = vol.cpu().numpy().view(np.uint16)
+    del vol
+    torch.cuda.empty_cache()
+    _, _, hst = stack_detect.detect_blobs_blocks(
+        str(tmp_path / "c2h"), np_io.Image5d(host[None]), None, None, [0], False, False, True)
+    np.testing.assert_array_equal(res.blobs, hst.blobs)
+    b = res.blobs
+    assert b.shape[1] == 8 and len(b) > 200_000
+    assert np.all(b[:, :3] >= 0) and np.all(b[:, :3] < np.array(shape))
+    # integer coordinates (seam averages are rounded), radii from the sigma ladder only
+    assert np.all(b[:, :3] == np.round(b[:, :3]))
+    radii = np.unique(np.round(b[:, 3], 9))
+    assert len(radii) <= 10 and radii.min() >= 3 * np.sqrt(3) - 1e-6 and radii.max() <= 5 * np.sqrt(3) + 1e-6
