@@ -186,7 +186,7 @@ class StackDetector(object):
     @classmethod
     def detect_blobs_sub_rois_device(cls, img, sub_roi_slices, sub_rois_offsets,
                                      denoise_max_shape, channel, coords=None,
-                                     prefix=None, suffix=None):
+                                     prefix=None, suffix=None, tables=None):
         """``detect_blobs_sub_rois`` with the per-chunk tables left on the device:
         returns the merged (N, 14) float64 CUDA tensor of
         ``device_tables.ChunkTables.merged`` (None when nothing was found) instead
@@ -194,7 +194,10 @@ class StackDetector(object):
         caller falls back to the host route for that).  ``prefix`` / ``suffix``
         (device tensors of whole planes around a HOST ``img``, see
         ``gpu.StripFeeder``) let ``multi_gpu`` stream a rank's own planes from host
-        memory while the halo planes of its neighbours are already in HBM."""
+        memory while the halo planes of its neighbours are already in HBM.  With
+        ``tables`` (a ``device_tables.ChunkTables``) the survivors are appended to it
+        and it is returned unmerged, so several calls on different pieces of a
+        volume can feed one table."""
         from collections import deque
         from .. import gpu
         from . import device_tables
@@ -210,7 +213,9 @@ class StackDetector(object):
             cols = sorted({c[1] for c in todo})
             y_ranges = []
             for j in cols:
-                sy = sub_roi_slices[todo[0][0], j, todo[0][2]][1]
+                # every chunk of a column has the same y range; take it from one that is
+                # on this call's list (other cells of the grid may be placeholders)
+                sy = sub_roi_slices[next(c for c in todo if c[1] == j)][1]
                 y_ranges.append((sy.start, sy.stop))
             feeder = gpu.StripFeeder(img, y_ranges, prefix=prefix, suffix=suffix)
             todo.sort(key=lambda c: (c[1], c[0], c[2]))
@@ -224,7 +229,9 @@ class StackDetector(object):
         if n_chl > det.n_slots - 1:
             cls._gpu_detector = None
             cls._gpu_detector = det = gpu.ChunkDetector(det.max_shape, n_slots=2 * n_chl)
-        tables = device_tables.ChunkTables(det.device)
+        merge = tables is None
+        if tables is None:
+            tables = device_tables.ChunkTables(det.device)
         pending = deque()
 
         def finish_oldest():
@@ -256,7 +263,7 @@ class StackDetector(object):
             feeder.release(strip_of)
         while pending:
             finish_oldest()
-        return tables.merged()
+        return tables.merged() if merge else tables
 
     @classmethod
     def detect_blobs_sub_rois(cls, img5d, img, sub_roi_slices, sub_rois_offsets,

@@ -331,10 +331,56 @@ def chunk_row_plan(global_shape: Sequence[int], blocks, held: Sequence[Range]):
     return rows, z_bounds, wanted
 
 
+def loan_units(rows: Sequence[Sequence[int]], z_bounds: Sequence[Range],
+               y_bounds: Sequence[Range]) -> List[Tuple[int, int, int, int]]:
+    """Even out the row-wise dealing by lending single (chunk z-row k, chunk y-column j)
+    units - the five or so chunks of one row that share a y range - from the most to
+    the least loaded rank while that lowers the maximum load.  ceil(N*512/500) chunk
+    rows never split evenly over N ranks (601 vs 505 planes at N = 8); whole rows keep
+    the plane traffic between slab neighbours, and only the odd row travels as
+    sub-boxes.  Returns ``(k, j, owner, worker)`` tuples, deterministic."""
+    world = len(rows)
+    weight = lambda k, j: (z_bounds[k][1] - z_bounds[k][0]) * (y_bounds[j][1] - y_bounds[j][0])
+    units = {r: [(k, j) for k in rows[r] for j in range(len(y_bounds))] for r in range(world)}
+    owner = {u: r for r in range(world) for u in units[r]}
+    load = [sum(weight(*u) for u in units[r]) for r in range(world)]
+    loans = []
+    for _ in range(4 * world * len(y_bounds)):
+        hi = max(range(world), key=lambda r: (load[r], -r))
+        lo = min(range(world), key=lambda r: (load[r], r))
+        gap = load[hi] - load[lo]
+        # the unit whose move brings the two loads closest; moving w helps iff w < gap
+        cands = [u for u in units[hi] if weight(*u) < gap]
+        if not cands:
+            break
+        u = min(cands, key=lambda u: (abs(gap - 2 * weight(*u)), u))
+        units[hi].remove(u)
+        units[lo].append(u)
+        load[hi] -= weight(*u)
+        load[lo] += weight(*u)
+        loans = [l for l in loans if (l[0], l[1]) != u]
+        if owner[u] != lo:
+            loans.append((u[0], u[1], owner[u], lo))
+    return sorted(loans)
+
+
+def box_transfer_plan(loans, z_bounds, y_bounds, held):
+    """``(src, dst, k, j, z0, z1)`` for every piece of a lent unit's box: the planes
+    [z0, z1) of chunk row k held by ``src``, restricted to chunk column j's y range,
+    needed by worker ``dst`` (src == dst: the worker holds those planes itself)."""
+    plan = []
+    for k, j, _, worker in loans:
+        for src, (h0, h1) in enumerate(held):
+            z0, z1 = max(z_bounds[k][0], h0), min(z_bounds[k][1], h1)
+            if z0 < z1:
+                plan.append((src, worker, k, j, z0, z1))
+    return plan
+
+
 def detect_blobs_blocks_slabs(filename_base: str, slab, held: Sequence[Range],
                               global_shape: Sequence[int],
                               channels: Optional[Sequence[int]] = None, group=None,
-                              save_dfs: bool = False):
+                              save_dfs: bool = False, balance_units: bool = True):
     """``stack_detect.detect_blobs_blocks`` over a volume sharded as z-slabs.
 
     Args:
@@ -359,6 +405,11 @@ def detect_blobs_blocks_slabs(filename_base: str, slab, held: Sequence[Range],
     shape = tuple(int(v) for v in global_shape[:3]) + tuple(slab.shape[3:])
     blocks = stack_detect.setup_blocks(settings, shape)
     rows, z_bounds, wanted = chunk_row_plan(shape, blocks, held)
+    grid = blocks.sub_roi_slices.shape
+    y_bounds = [(blocks.sub_roi_slices[0, j, 0][1].start, blocks.sub_roi_slices[0, j, 0][1].stop)
+                for j in range(grid[1])]
+    loans = loan_units(rows, z_bounds, y_bounds) if balance_units else []
+    lent = {(k, j) for k, j, _, _ in loans}
     host_slab = isinstance(slab, np.ndarray)
     streamed = (host_slab and slab.flags.c_contiguous and blocks.exclude_border is None
                 and stack_detect.DEVICE_TABLES)
@@ -375,11 +426,12 @@ def detect_blobs_blocks_slabs(filename_base: str, slab, held: Sequence[Range],
     w0 = wanted[rank][0]
     final_on_device = False
 
-    grid = blocks.sub_roi_slices.shape
     local_slices = np.empty(grid, dtype=object)
     coords = []
     for k in rows[rank]:
         for j in range(grid[1]):
+            if (k, j) in lent:
+                continue                      # worked on by another rank (loan_units)
             for i in range(grid[2]):
                 sz, sy, sx = blocks.sub_roi_slices[k, j, i]
                 local_slices[k, j, i] = (slice(sz.start - w0, sz.stop - w0), sy, sx)
@@ -392,19 +444,38 @@ def detect_blobs_blocks_slabs(filename_base: str, slab, held: Sequence[Range],
         # device-resident tables: the gather moves CUDA tensors over NVLink and rank 0
         # prunes the seams on its GPU
         from .cv import device_tables
-        merged = None
+        dev = torch.device("cuda", torch.cuda.current_device()) if host_slab else slab.device
+        boxes = _exchange_boxes(slab, held, loans, z_bounds, y_bounds, group, dev)
+        tables = device_tables.ChunkTables(dev)
         if coords:
-            merged = stack_detect.StackDetector.detect_blobs_sub_rois_device(
+            stack_detect.StackDetector.detect_blobs_sub_rois_device(
                 ext, local_slices, blocks.sub_rois_offsets, blocks.denoise_max_shape,
-                channels, coords=coords, prefix=prefix, suffix=suffix)
-        parts = gather_tensor_rows(
-            merged, device_tables.N_MERGED, group,
-            device=torch.device("cuda", torch.cuda.current_device()) if host_slab else slab.device)
+                channels, coords=coords, prefix=prefix, suffix=suffix, tables=tables)
+        for (k, j), box in boxes.items():
+            # a lent unit: the chunks (k, j, :) cut from their own small box
+            box_slices = np.empty(grid, dtype=object)
+            for c in np.ndindex(*grid):
+                box_slices[c] = (slice(0, 0), slice(0, 0), slice(0, 0))
+            unit = []
+            for i in range(grid[2]):
+                sz, sy, sx = blocks.sub_roi_slices[k, j, i]
+                box_slices[k, j, i] = (slice(0, sz.stop - sz.start), slice(0, sy.stop - sy.start), sx)
+                unit.append((k, j, i))
+            stack_detect.StackDetector.detect_blobs_sub_rois_device(
+                box, box_slices, blocks.sub_rois_offsets, blocks.denoise_max_shape, channels,
+                coords=unit, tables=tables)
+        merged = tables.merged()
+        parts = gather_tensor_rows(merged, device_tables.N_MERGED, group, device=dev)
         if rank != 0:
             return None, None, None
-        # runs of chunk rows are contiguous and in rank order = chunk-grid order
+        allm = torch.cat(parts)
+        if loans and allm.shape[0]:
+            # lent units arrive with their worker's table: restore chunk-grid order
+            tg = allm[:, 11:14].long()
+            key = (tg[:, 0] * grid[1] + tg[:, 1]) * grid[2] + tg[:, 2]
+            allm = allm[torch.sort(key, stable=True).indices]
         segments_all, df_pruning = device_tables.prune_merged(
-            torch.cat(parts), blocks.overlap, blocks.tol, blocks.sub_roi_slices,
+            allm, blocks.overlap, blocks.tol, blocks.sub_roi_slices,
             blocks.sub_rois_offsets, channels, blocks.overlap_padding, final_layout=True)
         final_on_device = True
     else:
@@ -440,6 +511,61 @@ def detect_blobs_blocks_slabs(filename_base: str, slab, held: Sequence[Range],
     if save_dfs and df_pruning is not None and len(df_pruning.columns):
         df_pruning.to_csv("blob_ratios.csv", index=False)
     return None, None, blobs
+
+
+def _exchange_boxes(slab, held, loans, z_bounds, y_bounds, group, dev) -> Dict[tuple, torch.Tensor]:
+    """Move the sub-boxes of lent units to their workers (NCCL send/recv of dense
+    copies; from a host slab the pieces go up with one pitched DMA each).  Returns
+    ``{(k, j): box}`` for the units this rank works on."""
+    rank, world = _world(group)
+    if not loans:
+        return {}
+    host_slab = isinstance(slab, np.ndarray)
+    h0 = held[rank][0]
+    if host_slab:
+        tdtype = torch.int16 if slab.dtype == np.uint16 else torch.from_numpy(slab[:0]).dtype
+    else:
+        tdtype = slab.dtype
+    tail = tuple(slab.shape[2:])
+    boxes = {}
+    for k, j, _, worker in loans:
+        if worker == rank:
+            boxes[(k, j)] = torch.empty(
+                (z_bounds[k][1] - z_bounds[k][0], y_bounds[j][1] - y_bounds[j][0]) + tail,
+                dtype=tdtype, device=dev)
+
+    def piece(z0, z1, y0, y1):
+        if not host_slab:
+            return slab[z0 - h0:z1 - h0, y0:y1].contiguous()
+        from . import gpu, _lib
+        import ctypes as C
+        out = torch.empty((z1 - z0, y1 - y0) + tail, dtype=tdtype, device=dev)
+        row_bytes = int(np.prod(tail)) * slab.itemsize
+        src = slab.ctypes.data + ((z0 - h0) * slab.shape[1] + y0) * row_bytes
+        _lib.check(_lib.load().mmb_upload_pieces(
+            C.c_void_p(out.data_ptr()), C.c_void_p(src), z1 - z0, (y1 - y0) * row_bytes,
+            slab.shape[1] * row_bytes, gpu._stream()))
+        return out
+
+    g = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+    ops, keep = [], []
+    for src, dst, k, j, z0, z1 in box_transfer_plan(loans, z_bounds, y_bounds, held):
+        y0, y1 = y_bounds[j]
+        if src == rank and dst == rank:
+            boxes[(k, j)][z0 - z_bounds[k][0]:z1 - z_bounds[k][0]].copy_(piece(z0, z1, y0, y1))
+        elif src == rank:
+            buf = piece(z0, z1, y0, y1).view(torch.uint8)
+            keep.append(buf)
+            ops.append(dist.P2POp(dist.isend, buf, g(dst), group))
+        elif dst == rank:
+            view = boxes[(k, j)][z0 - z_bounds[k][0]:z1 - z_bounds[k][0]]   # whole planes of the box
+            ops.append(dist.P2POp(dist.irecv, view.view(torch.uint8), g(src), group))
+    if ops:
+        if host_slab:
+            torch.cuda.current_stream().synchronize()      # uploads done before NCCL reads them
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return boxes
 
 
 def _agree_max(v: int, group=None) -> int:

@@ -71,6 +71,34 @@ def test_chunk_rows_balanced_and_wanted_ranges():
     assert sorted(k for r in r3 for k in r) == [0, 1, 2] and max(len(r) for r in r3) == 1
 
 
+def test_loan_units_even_out_the_odd_row():
+    """N slabs of 512 planes make ceil(N*512/500) chunk rows; lending (row, y-column)
+    units brings every rank within 1 % of the mean load, each unit keeps exactly one
+    worker, and the box plan covers every plane of a lent unit exactly once."""
+    for n in (2, 4, 8):
+        Z = 512 * n
+        zb = [(500 * k, min(500 * k + 505, Z)) for k in range(-(-Z // 500))]
+        yb = [(500 * j, min(500 * j + 505, 2048)) for j in range(5)]
+        held = mg.slab_bounds(Z, n)
+        rows = mg.assign_chunk_rows_balanced(zb, n)
+        loans = mg.loan_units(rows, zb, yb)
+        assert len({(k, j) for k, j, _, _ in loans}) == len(loans)
+        w = lambda k, j: (zb[k][1] - zb[k][0]) * (yb[j][1] - yb[j][0])
+        load = [sum(w(k, j) for k in rows[r] for j in range(5)) for r in range(n)]
+        before = max(load) / (sum(load) / n)
+        for k, j, owner, worker in loans:
+            assert k in rows[owner] and owner != worker
+            load[owner] -= w(k, j)
+            load[worker] += w(k, j)
+        assert max(load) / (sum(load) / n) < 1.01 < before
+        plan = mg.box_transfer_plan(loans, zb, yb, held)
+        for k, j, _, worker in loans:
+            pieces = sorted((z0, z1) for s, d, kk, jj, z0, z1 in plan if (kk, jj, d) == (k, j, worker))
+            assert pieces[0][0] == zb[k][0] and pieces[-1][1] == zb[k][1]
+            assert all(a[1] == b[0] for a, b in zip(pieces[:-1], pieces[1:]))
+    assert mg.loan_units([[0, 1, 2]], [(0, 505), (500, 1005), (1000, 1024)], [(0, 505)]) == []
+
+
 def test_seamless_plan_halo_is_whole_block_layers():
     own, ext = mg.seamless_plan(1024, 2, 25, 21)
     assert own == [(0, 500), (500, 1024)] and ext == [(0, 525), (475, 1024)]
