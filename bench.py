@@ -417,8 +417,9 @@ def main():
                    "blobs_per_step": n_blobs, "host_stage_s_last_step": stage_times,
                    "multi_gpu": None if world == 1 else
                    f"{world} z-slabs of one {gshape[0]}x{gshape[1]}x{gshape[2]} volume, chunk rows "
-                   f"dealt to the slab of their first plane, halo planes by NCCL send/recv, "
-                   f"tables gathered to rank 0 and seam-pruned there"},
+                   f"dealt in balanced runs (single row x y-column units lent between ranks), "
+                   f"halo planes and lent sub-boxes by NCCL send/recv, device tables gathered "
+                   f"to rank 0 and seam-pruned there"},
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
         "clocks": clocks,
     }

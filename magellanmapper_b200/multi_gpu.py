@@ -331,16 +331,30 @@ def chunk_row_plan(global_shape: Sequence[int], blocks, held: Sequence[Range]):
     return rows, z_bounds, wanted
 
 
+#: fixed cost of one chunk in voxel equivalents (launch gaps and kernel tails of about
+#: 45 launches): on a B200 the 34 thin chunks of config 2 (86 MVoxel) take 47 ms where
+#: 0.141 ms/MVoxel would predict 12 ms, i.e. about 1 ms = 7 MVoxel per chunk
+CHUNK_OVERHEAD_VOXELS = 7.0e6
+
+
 def loan_units(rows: Sequence[Sequence[int]], z_bounds: Sequence[Range],
-               y_bounds: Sequence[Range]) -> List[Tuple[int, int, int, int]]:
+               y_bounds: Sequence[Range], x_bounds: Optional[Sequence[Range]] = None
+               ) -> List[Tuple[int, int, int, int]]:
     """Even out the row-wise dealing by lending single (chunk z-row k, chunk y-column j)
     units - the five or so chunks of one row that share a y range - from the most to
     the least loaded rank while that lowers the maximum load.  ceil(N*512/500) chunk
     rows never split evenly over N ranks (601 vs 505 planes at N = 8); whole rows keep
     the plane traffic between slab neighbours, and only the odd row travels as
-    sub-boxes.  Returns ``(k, j, owner, worker)`` tuples, deterministic."""
+    sub-boxes.  The load of a unit is its voxel count plus, when ``x_bounds`` names its
+    chunks, ``CHUNK_OVERHEAD_VOXELS`` per chunk.  Returns ``(k, j, owner, worker)``
+    tuples, deterministic."""
     world = len(rows)
-    weight = lambda k, j: (z_bounds[k][1] - z_bounds[k][0]) * (y_bounds[j][1] - y_bounds[j][0])
+
+    def weight(k, j):
+        area = (z_bounds[k][1] - z_bounds[k][0]) * (y_bounds[j][1] - y_bounds[j][0])
+        if x_bounds is None:
+            return float(area)
+        return sum(area * (b - a) + CHUNK_OVERHEAD_VOXELS for a, b in x_bounds)
     units = {r: [(k, j) for k in rows[r] for j in range(len(y_bounds))] for r in range(world)}
     owner = {u: r for r in range(world) for u in units[r]}
     load = [sum(weight(*u) for u in units[r]) for r in range(world)]
@@ -408,7 +422,9 @@ def detect_blobs_blocks_slabs(filename_base: str, slab, held: Sequence[Range],
     grid = blocks.sub_roi_slices.shape
     y_bounds = [(blocks.sub_roi_slices[0, j, 0][1].start, blocks.sub_roi_slices[0, j, 0][1].stop)
                 for j in range(grid[1])]
-    loans = loan_units(rows, z_bounds, y_bounds) if balance_units else []
+    x_bounds = [(blocks.sub_roi_slices[0, 0, i][2].start, blocks.sub_roi_slices[0, 0, i][2].stop)
+                for i in range(grid[2])]
+    loans = loan_units(rows, z_bounds, y_bounds, x_bounds) if balance_units else []
     lent = {(k, j) for k, j, _, _ in loans}
     host_slab = isinstance(slab, np.ndarray)
     streamed = (host_slab and slab.flags.c_contiguous and blocks.exclude_border is None
