@@ -82,15 +82,12 @@ def make_device_volume(shape, seed, device, z_offset=0, z_total=None):
 
 
 def near_max_device(vol_i16):
-    """max over z-planes of the per-plane 99.5th percentile (importer metadata)."""
-    import torch
-    best = 0.0
-    for z in range(0, vol_i16.shape[0], max(1, vol_i16.shape[0] // 32)):
-        p = vol_i16[z].to(torch.int32)
-        p = torch.where(p < 0, p + 65536, p).float().flatten()
-        k = int(0.995 * (p.numel() - 1))
-        best = max(best, float(torch.kthvalue(p, k + 1).values))
-    return best
+    """The importer's ``near_max`` metadata: max over z-planes of the per-plane 99.5th
+    percentile (magmap/io/importer.py:571-583), computed on the device by
+    ``mmb_percentiles`` (every plane, exact)."""
+    from magellanmapper_b200.io import importer
+    _, near_maxs = importer.calc_near_bounds(vol_i16)
+    return float(np.ravel(near_maxs)[0])
 
 
 # ----------------------------------------------------------------------------

@@ -69,6 +69,21 @@ const char* mmb_last_error(void);
 int mmb_upload_pieces(void* dst_device, const void* src_host, int64_t planes,
                       int64_t piece_bytes, int64_t src_pitch_bytes, void* stream);
 
+/* ---- import metadata: intensity bounds ------------------------------------------
+ * Replaces the np.percentile calls behind the image metadata `near_min` /
+ * `near_max` that saturate_roi consumes (magmap/io/importer.py:1368-1377 and
+ * :571-583 per z-plane, calc_intensity_bounds :1415-1444 over a whole array;
+ * numpy 'linear' method, float64): out[g * nq + i] = percentile q_percent[i] of
+ * group g, where a group is one z-plane (`per_plane` != 0, Z groups) or the whole
+ * (Z, Y, X) view (one group).  uint8 / uint16 input with element strides, so one
+ * channel of a channel-last array is read in place; other dtypes return
+ * MMB_ERR_UNSUPPORTED.  `out_device` holds groups * nq doubles, `work`
+ * mmb_percentiles_work_bytes(groups) bytes.  Asynchronous on `stream`.             */
+int64_t mmb_percentiles_work_bytes(int n_groups);
+int mmb_percentiles(const void* in, int dtype, const int64_t in_strides[3],
+                    int Z, int Y, int X, int per_plane, const double* q_percent,
+                    int nq, double* out_device, void* work, void* stream);
+
 /* ---- img_as_float ---------------------------------------------------------
  * Replaces skimage.util.img_as_float inside blob_log (reference call site
  * magmap/cv/detector.py:931): out = in * scale, element strides given per axis

@@ -53,6 +53,9 @@ SIGNATURES = {
     "mmb_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64),
                                       C.POINTER(C.c_double)]),
     "mmb_upload_pieces": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, C.c_int64, _vp]),
+    "mmb_percentiles_work_bytes": (C.c_int64, [C.c_int]),
+    "mmb_percentiles": (C.c_int, [_vp, C.c_int, _I64x3, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.POINTER(C.c_double), C.c_int, _vp, _vp, _vp]),
     "mmb_to_float": (C.c_int, [_vp, C.c_int, _I64x3, C.c_int, C.c_int, C.c_int, _vp,
                                C.c_int64, C.c_double, _vp]),
     "mmb_preprocess_blocks": (C.c_int, [_vp, C.c_int, _I64x3, C.c_int, C.c_int, C.c_int,

@@ -203,6 +203,23 @@ class StripFeeder:
             self._issue(nxt)
 
 
+def percentiles(src: Source, q: Sequence[float], per_plane: bool = False) -> np.ndarray:
+    """``np.percentile(view, q)`` ('linear', float64) of a uint8 / uint16 view on the
+    device: shape ``(len(q),)`` for the whole view, ``(Z, len(q))`` per z-plane."""
+    lib = _lib.load()
+    Z, Y, X = src.shape
+    groups = Z if per_plane else 1
+    dev = src.tensor.device
+    out = torch.empty((groups, len(q)), dtype=torch.float64, device=dev)
+    work = torch.empty(lib.mmb_percentiles_work_bytes(groups), dtype=torch.uint8, device=dev)
+    qs = (C.c_double * len(q))(*[float(v) for v in q])
+    _lib.check(lib.mmb_percentiles(C.c_void_p(src.ptr), src.dtype, _lib._I64x3(*src.strides), Z, Y, X,
+                                   1 if per_plane else 0, qs, len(q), _ptr(out), _ptr(work),
+                                   _stream()))
+    res = out.cpu().numpy()
+    return res if per_plane else res[0]
+
+
 def to_float(src: Source, scale: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     lib = _lib.load()
     Z, Y, X = src.shape

@@ -430,3 +430,30 @@ def detect_blobs_blocks(img: np.ndarray, prof: Profile, resolution,
     if return_parts:
         return final, seg_rois, blocks
     return final
+
+
+# ---- import metadata: intensity bounds (magmap/io/importer.py) ---------------------
+
+def calc_intensity_bounds(image, lower=0.5, upper=99.5, channel_axis=None):
+    """``importer.calc_intensity_bounds`` (importer.py:1415-1444): np.percentile of the
+    whole array, per channel when ``channel_axis`` is given."""
+    if channel_axis is None:
+        low, high = np.percentile(image, (lower, upper))
+        return [low], [high]
+    lows, highs = [], []
+    for c in range(image.shape[channel_axis]):
+        low, high = np.percentile(np.take(image, c, axis=channel_axis), (lower, upper))
+        lows.append(low)
+        highs.append(high)
+    return lows, highs
+
+
+def calc_near_bounds(image, multichannel=False):
+    """Per-plane bounds reduced over the planes (importer.py:571-583, 1447-1468) of a
+    (z, y, x[, c]) image: ``(near_mins, near_maxs)`` as 1-D float64 arrays per channel."""
+    lows, highs = [], []
+    for z in range(image.shape[0]):
+        lo, hi = calc_intensity_bounds(image[z], channel_axis=2 if multichannel else None)
+        lows.append(lo)
+        highs.append(hi)
+    return np.amin(np.array(lows), 0), np.amax(np.array(highs), 0)

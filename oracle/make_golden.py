@@ -254,5 +254,43 @@ def main():
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
+def make_near_bounds():
+    """importer.calc_intensity_bounds / calc_near_intensity_bounds of the UNMODIFIED
+    reference on small uint16 / uint8 volumes (one and two channels)."""
+    ref_shim.load_reference()
+    from magmap.io import importer
+    rng = np.random.default_rng(21)
+    out = {}
+    vols = {
+        "u16": rng.integers(0, 65535, (6, 41, 37)).astype(np.uint16),
+        "u16_narrow": (400 + 30 * rng.standard_normal((5, 64, 50))).clip(0, 65535).astype(np.uint16),
+        "u8": rng.integers(0, 255, (4, 30, 33)).astype(np.uint8),
+        "u16_2c": rng.integers(0, 4000, (5, 28, 31, 2)).astype(np.uint16),
+    }
+    for name, vol in vols.items():
+        multichannel = vol.ndim == 4
+        lows, highs = [], []
+        for z in range(vol.shape[0]):
+            lo, hi = importer.calc_intensity_bounds(vol[z], dim_channel=2)
+            lows.append(lo)
+            highs.append(hi)
+        near_mins, near_maxs = importer.calc_near_intensity_bounds([], [], lows, highs)
+        whole_lo, whole_hi = importer.calc_intensity_bounds(vol[None], dim_channel=4)
+        out[f"{name}_vol"] = vol
+        out[f"{name}_plane_lows"] = np.array(lows, dtype=np.float64)
+        out[f"{name}_plane_highs"] = np.array(highs, dtype=np.float64)
+        out[f"{name}_near_mins"] = np.array(near_mins, dtype=np.float64)
+        out[f"{name}_near_maxs"] = np.array(near_maxs, dtype=np.float64)
+        out[f"{name}_whole"] = np.array([whole_lo, whole_hi], dtype=np.float64)
+        out[f"{name}_multichannel"] = np.array(multichannel)
+    np.savez_compressed(os.path.join(OUT, "near_bounds.npz"), **out)
+    print("near_bounds.npz:", {k: v.shape for k, v in out.items() if not k.endswith("_vol")})
+
+
 if __name__ == "__main__":
-    main()
+    import sys as _sys
+    if len(_sys.argv) > 1 and _sys.argv[1] == "near_bounds":
+        make_near_bounds()          # only the vectors added after the first batch
+    else:
+        main()
+        make_near_bounds()

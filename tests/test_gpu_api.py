@@ -238,3 +238,40 @@ def test_config2_full_size_resident_equals_streamed(tmp_path):
     assert np.all(b[:, :3] == np.round(b[:, :3]))
     radii = np.unique(np.round(b[:, 3], 9))
     assert len(radii) <= 10 and radii.min() >= 3 * np.sqrt(3) - 1e-6 and radii.max() <= 5 * np.sqrt(3) + 1e-6
+
+
+def test_near_bounds_on_device_vs_reference_vectors(golden_dir):
+    """io.importer on the GPU (mmb_percentiles) against the unmodified reference's
+    importer.calc_intensity_bounds / calc_near_intensity_bounds: bit-equal float64 for
+    uint16, a narrow-histogram uint16, uint8 and a two-channel channel-last volume."""
+    from magellanmapper_b200.io import importer
+    g = np.load(os.path.join(golden_dir, "near_bounds.npz"))
+    for name in ("u16", "u16_narrow", "u8", "u16_2c"):
+        vol = g[f"{name}_vol"]
+        lows, highs = importer.calc_plane_bounds(vol)
+        np.testing.assert_array_equal(np.array(lows), g[f"{name}_plane_lows"])
+        np.testing.assert_array_equal(np.array(highs), g[f"{name}_plane_highs"])
+        near_mins, near_maxs = importer.calc_near_bounds(vol)
+        np.testing.assert_array_equal(np.ravel(near_mins), np.ravel(g[f"{name}_near_mins"]))
+        np.testing.assert_array_equal(np.ravel(near_maxs), np.ravel(g[f"{name}_near_maxs"]))
+        lo, hi = importer.calc_intensity_bounds(vol[None], dim_channel=4)
+        np.testing.assert_array_equal(np.array([lo, hi]), g[f"{name}_whole"])
+        # device-resident input is read in place
+        t = torch.from_numpy(vol.view(np.int16) if vol.dtype == np.uint16 else vol).cuda()
+        m2, x2 = importer.calc_near_bounds(t)
+        np.testing.assert_array_equal(np.ravel(m2), np.ravel(near_mins))
+    with pytest.raises(NotImplementedError):
+        importer.calc_near_bounds(np.zeros((2, 8, 8), np.float32))
+
+
+def test_near_max_of_config2_plane_sized_input():
+    """A 2048x2048 plane stack: per-plane percentiles equal numpy's on planes with
+    4.2 M samples (counts beyond 16 bits, ranks that fall between duplicates)."""
+    from magellanmapper_b200.io import importer
+    rng = np.random.default_rng(8)
+    vol = (400 + 30 * rng.standard_normal((3, 2048, 2048))).clip(0, 65535).astype(np.uint16)
+    vol[1, :64] = 60000
+    lows, highs = importer.calc_plane_bounds(vol)
+    for z in range(3):
+        lo, hi = np.percentile(vol[z], (0.5, 99.5))
+        assert lows[z][0] == lo and highs[z][0] == hi

@@ -140,3 +140,18 @@ def test_prune_order_dependence_is_characterised(golden_dir):
         _, tr2 = ski.prune_blobs(lm, 0.5, trace=True, pair_order=tr.pairs[perm])
         d = np.nonzero(tr2.keep_reference_order != base)[0]
         assert set(d.tolist()) <= set(tr.order_dependent.tolist())
+
+
+def test_near_bounds_oracle_vs_reference(golden_dir):
+    """oracle.calc_intensity_bounds / calc_near_bounds against the unmodified
+    reference's importer functions (tests/golden/near_bounds.npz)."""
+    from oracle import magmap_restated as mm
+    g = np.load(os.path.join(golden_dir, "near_bounds.npz"))
+    for name in ("u16", "u16_narrow", "u8", "u16_2c"):
+        vol = g[f"{name}_vol"]
+        multichannel = bool(g[f"{name}_multichannel"])
+        near_mins, near_maxs = mm.calc_near_bounds(vol, multichannel)
+        np.testing.assert_array_equal(np.ravel(near_mins), np.ravel(g[f"{name}_near_mins"]))
+        np.testing.assert_array_equal(np.ravel(near_maxs), np.ravel(g[f"{name}_near_maxs"]))
+        lo, hi = mm.calc_intensity_bounds(vol, channel_axis=3 if multichannel else None)
+        np.testing.assert_array_equal(np.array([lo, hi]), g[f"{name}_whole"])

@@ -78,6 +78,8 @@ def main():
         rows.append(r)
         print(json.dumps(r))
 
+    ms = timeit(lambda: gpu.percentiles(src, (0.5, 99.5), per_plane=True), args.reps)
+    report("percentiles per plane (0.5, 99.5)", ms, 4.0)
     ms = timeit(lambda: gpu.preprocess_blocks(src, (25, 25, 25), pre, out=F), args.reps)
     report("preprocess_25^3", ms, 6.0)
     ms = timeit(lambda: gpu.to_float(src, 1 / 65535.0, out=torch.empty_like(F)), args.reps)
