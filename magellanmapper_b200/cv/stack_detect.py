@@ -211,6 +211,13 @@ class StackDetector(object):
         if (isinstance(img, np.ndarray) and img.flags.c_contiguous and img.dtype in gpu._NP2MMB
                 and todo):
             cols = sorted({c[1] for c in todo})
+            # the narrowest strip goes first: its upload is the only one nothing can
+            # hide, and its kernels then cover part of the first wide strip's upload
+            if len(cols) > 1:
+                width = {j: (lambda sy: sy.stop - sy.start)(
+                    sub_roi_slices[next(c for c in todo if c[1] == j)][1]) for j in cols}
+                first = min(cols, key=lambda j: (width[j], j))
+                cols = [first] + [j for j in cols if j != first]
             y_ranges = []
             for j in cols:
                 # every chunk of a column has the same y range; take it from one that is
@@ -218,7 +225,7 @@ class StackDetector(object):
                 sy = sub_roi_slices[next(c for c in todo if c[1] == j)][1]
                 y_ranges.append((sy.start, sy.stop))
             feeder = gpu.StripFeeder(img, y_ranges, prefix=prefix, suffix=suffix)
-            todo.sort(key=lambda c: (c[1], c[0], c[2]))
+            todo.sort(key=lambda c: (cols.index(c[1]), c[0], c[2]))
         else:
             if prefix is not None or suffix is not None:
                 raise ValueError("prefix/suffix planes need a C-contiguous host image")
