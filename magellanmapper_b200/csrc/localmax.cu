@@ -92,10 +92,11 @@ localmax_kernel(const float* __restrict__ prev, const float* __restrict__ cur,
   }
   const bool owner = lane >= 1 && lane <= 30;
 
+  // phase 1 (unrolled, registers only): one bit per (row, column) that is above the
+  // threshold and not beaten inside its 3x3 in-plane neighbourhood
+  unsigned mask = 0;
 #pragma unroll
   for (int r = 1; r <= kLmRows; ++r) {
-    const int y = y0 + r - 1;
-    if (y >= Y) break;                                   // warp-uniform
     // vertical maxima of rows r-1, r, r+1
     const float c0 = fmaxf(fmaxf(v[r - 1].x, v[r].x), v[r + 1].x);
     const float c1 = fmaxf(fmaxf(v[r - 1].y, v[r].y), v[r + 1].y);
@@ -108,33 +109,42 @@ localmax_kernel(const float* __restrict__ prev, const float* __restrict__ cur,
     const float m1 = fmaxf(fmaxf(c0, c1), c2);
     const float m2 = fmaxf(fmaxf(c1, c2), c3);
     const float m3 = fmaxf(fmaxf(c2, c3), cr);
-    const float vs[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
-    const float ms[4] = {m0, m1, m2, m3};
-    unsigned cand = 0;
-    if (owner) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (vs[k] > thr && !(ms[k] > vs[k])) cand |= 1u << k;
+    unsigned bits = 0;
+    if (v[r].x > thr && !(m0 > v[r].x)) bits |= 1u;
+    if (v[r].y > thr && !(m1 > v[r].y)) bits |= 2u;
+    if (v[r].z > thr && !(m2 > v[r].z)) bits |= 4u;
+    if (v[r].w > thr && !(m3 > v[r].w)) bits |= 8u;
+    if (y0 + r - 1 < Y) mask |= bits << (4 * (r - 1));
+  }
+  if (!owner) mask = 0;
+
+  // phase 2 (a loop, not unrolled: the straight-line form of this kernel was 58 KB of
+  // code and stalled on instruction fetch): the few in-plane maxima are re-read from
+  // memory (an L1 hit) and tested against the planes above and below and the two
+  // adjacent scales; survivors are compacted with a warp ballot
+  while (__any_sync(0xffffffffu, mask != 0)) {
+    bool peak = false;
+    int y = 0, x = 0;
+    float val = 0.f;
+    if (mask) {
+      const int bit = __ffs(mask) - 1;
+      mask &= mask - 1;
+      y = y0 + (bit >> 2);
+      x = x0 + (bit & 3);
+      val = __ldg(plane + (int64_t)y * pitch + x);
+      peak = survives_3d_and_scales(prev, cur, next, Z, Y, X, pitch, z, y, x, val);
     }
-    if (!__any_sync(0xffffffffu, cand != 0)) continue;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (!__any_sync(0xffffffffu, (cand >> k) & 1u)) continue;
-      bool peak = false;
-      if (cand & (1u << k))
-        peak = survives_3d_and_scales(prev, cur, next, Z, Y, X, pitch, z, y, x0 + k, vs[k]);
-      const unsigned ballot = __ballot_sync(0xffffffffu, peak);
-      if (ballot) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(counter, __popc(ballot));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (peak) {
-          const int idx = base + __popc(ballot & ((1u << lane) - 1u));
-          if (idx < capacity) {
-            mmb_cand c;
-            c.z = z; c.y = y; c.x = x0 + k; c.s = s; c.resp = vs[k];
-            out[idx] = c;
-          }
+    const unsigned ballot = __ballot_sync(0xffffffffu, peak);
+    if (ballot) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(counter, __popc(ballot));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (peak) {
+        const int idx = base + __popc(ballot & ((1u << lane) - 1u));
+        if (idx < capacity) {
+          mmb_cand c;
+          c.z = z; c.y = y; c.x = x; c.s = s; c.resp = val;
+          out[idx] = c;
         }
       }
     }
