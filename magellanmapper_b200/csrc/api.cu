@@ -127,17 +127,17 @@ int sort_by_z_enqueue(const mmb_cand* cand, const int* n_ptr, int n_max, int Z, 
 __global__ void compact_kernel(const mmb_cand* __restrict__ in, const uint8_t* __restrict__ keep,
                                const int* __restrict__ n_ptr, int n_max,
                                mmb_cand* __restrict__ out, int* __restrict__ counter) {
-  const int n = min(*n_ptr, n_max);
+  const int n = min(__ldcg(n_ptr), n_max);
   if (blockIdx.x * blockDim.x >= n) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool k = i < n && keep[i];
+  const bool k = i < n && __ldcg(keep + i);
   const unsigned ballot = __ballot_sync(0xffffffffu, k);
   if (!ballot) return;
   const int lane = threadIdx.x & 31;
   int base = 0;
   if (lane == 0) base = atomicAdd(counter, __popc(ballot));
   base = __shfl_sync(0xffffffffu, base, 0);
-  if (k) out[base + __popc(ballot & ((1u << lane) - 1u))] = in[i];
+  if (k) out[base + __popc(ballot & ((1u << lane) - 1u))] = load_cand(in + i);
 }
 
 static inline int64_t align256(int64_t x) { return (x + 255) / 256 * 256; }

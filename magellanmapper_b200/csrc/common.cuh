@@ -49,6 +49,18 @@ __host__ __device__ __forceinline__ int clamp_index(int p, int n) {
   return p < 0 ? 0 : (p >= n ? n - 1 : p);
 }
 
+// Workspace buffers are rewritten chunk after chunk at the same addresses and chunks
+// may run on two streams at once, i.e. kernels of different chunks share an SM and its
+// L1.  Readers of such buffers therefore load through L2 (ld.global.cg): a line cached
+// in L1 by an earlier kernel must never be served to a later one.
+__device__ __forceinline__ mmb_cand load_cand(const mmb_cand* p) {
+  const int* q = reinterpret_cast<const int*>(p);
+  mmb_cand c;
+  c.z = __ldcg(q); c.y = __ldcg(q + 1); c.x = __ldcg(q + 2); c.s = __ldcg(q + 3);
+  c.resp = __int_as_float(__ldcg(q + 4));
+  return c;
+}
+
 constexpr int kMaxRadius = 64;   // templated fast paths cover radius <= 64
 
 // Sampled Gaussian g[k] and second derivative h[k] for k = 0..r (both even),

@@ -193,7 +193,8 @@ conv_x_tma_kernel(const __grid_constant__ CUtensorMap tm_in,
       tma_commit();
     }
   }
-  if (tid == 0) tma_wait_read<0>();
+  // the stores must have LANDED before the CTA exits: the y sweep reads them
+  if (tid == 0) tma_wait_all<0>();
 }
 
 // ---- warp-specialised x sweep ------------------------------------------------------
@@ -417,6 +418,8 @@ conv_x_ws_kernel(const __grid_constant__ CUtensorMap tm_in,
         mbar_arrive(&empty_out[o]);
       }
     }
+    // every store of this CTA has landed before it exits (the y sweep reads them)
+    if (lane == 0) tma_wait_all<0>();
   }
 }
 

@@ -63,7 +63,7 @@ prune_edges_kernel(const mmb_cand* __restrict__ cand, const int* __restrict__ n_
   __shared__ double sigmas[kMaxSigmas];
   // the candidate count lives on the device (no host round trip); the grid is
   // sized for the buffer capacity and surplus CTAs leave at once
-  const int n = min(*n_ptr, n_max);
+  const int n = min(__ldcg(n_ptr), n_max);
   if (blockIdx.x * kTile >= n) return;
   const int num_sigma = ladder.n;
   for (int k = threadIdx.x; k < num_sigma; k += kTile) sigmas[k] = ladder.s[k];
@@ -72,7 +72,7 @@ prune_edges_kernel(const mmb_cand* __restrict__ cand, const int* __restrict__ n_
   mmb_cand me;
   me.z = me.y = me.x = 0; me.s = 0; me.resp = 0.f;
   double my_sigma = 0.0;
-  if (i < n) { me = cand[i]; my_sigma = sigmas[me.s]; }
+  if (i < n) { me = load_cand(cand + i); my_sigma = sigmas[me.s]; }
   const double smax = sigmas[num_sigma - 1] > sigmas[0] ? sigmas[num_sigma - 1] : sigmas[0];
   // spheres can only touch when |d| <= (s1+s2)*sqrt(3) <= 2*smax*sqrt(3)
   const float cut = (float)(2.0 * smax * 1.7320508075688772) + 1.0f;
@@ -80,12 +80,13 @@ prune_edges_kernel(const mmb_cand* __restrict__ cand, const int* __restrict__ n_
   // candidates listed by ascending z (the global prune of the seamless mode): once
   // a tile starts farther above this block's last candidate than the cut-off, so
   // does every later tile
-  const int z_block_max = z_sorted ? cand[min(n, (int)(blockIdx.x + 1) * kTile) - 1].z : 0;
+  const int z_block_max =
+      z_sorted ? __ldcg(&cand[min(n, (int)(blockIdx.x + 1) * kTile) - 1].z) : 0;
   // tiles with j > i only: start at this block's own tile
   for (int j0 = blockIdx.x * kTile; j0 < n; j0 += kTile) {
     __syncthreads();
     const int jl = j0 + threadIdx.x;
-    if (jl < n) tile[threadIdx.x] = cand[jl];
+    if (jl < n) tile[threadIdx.x] = load_cand(cand + jl);
     __syncthreads();
     if (z_sorted && (float)(tile[0].z - z_block_max) > cut) break;      // block-uniform
     if (i >= n) continue;
@@ -124,8 +125,8 @@ prune_resolve_kernel(const int* __restrict__ n_ptr, int n_max, const int2* __res
                      unsigned char* __restrict__ state, unsigned char* __restrict__ mark,
                      unsigned char* __restrict__ keep) {
   __shared__ int remaining;
-  const int n = min(*n_ptr, n_max);
-  const int n_edges = min(*n_edges_ptr, edge_cap);
+  const int n = min(__ldcg(n_ptr), n_max);
+  const int n_edges = min(__ldcg(n_edges_ptr), edge_cap);
   for (int v = threadIdx.x; v < n; v += blockDim.x) state[v] = 0;
   __syncthreads();
   while (true) {
@@ -133,7 +134,7 @@ prune_resolve_kernel(const int* __restrict__ n_ptr, int n_max, const int2* __res
     if (threadIdx.x == 0) remaining = 0;
     __syncthreads();
     for (int e = threadIdx.x; e < n_edges; e += blockDim.x) {
-      const int2 kv = edges[e];
+      const int2 kv = __ldcg(&edges[e]);
       if (state[kv.y] == 0) {
         const unsigned char sk = state[kv.x];
         if (sk == 1) atomicOr((unsigned int*)(mark + (kv.y & ~3)), 1u << (8 * (kv.y & 3)));
@@ -167,9 +168,9 @@ prune_resolve_kernel(const int* __restrict__ n_ptr, int n_max, const int2* __res
 // kill-graph resolution does not depend on the listing order.
 __global__ void z_hist_kernel(const mmb_cand* __restrict__ cand, const int* __restrict__ n_ptr,
                               int n_max, int* __restrict__ hist) {
-  const int n = min(*n_ptr, n_max);
+  const int n = min(__ldcg(n_ptr), n_max);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) atomicAdd(&hist[cand[i].z], 1);
+  if (i < n) atomicAdd(&hist[__ldcg(&cand[i].z)], 1);
 }
 
 __global__ void __launch_bounds__(1024)
@@ -198,10 +199,10 @@ z_scan_kernel(int* __restrict__ hist, int Z) {
 __global__ void z_scatter_kernel(const mmb_cand* __restrict__ cand, const int* __restrict__ n_ptr,
                                  int n_max, int* __restrict__ cursor,
                                  mmb_cand* __restrict__ out) {
-  const int n = min(*n_ptr, n_max);
+  const int n = min(__ldcg(n_ptr), n_max);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    const mmb_cand c = cand[i];
+    const mmb_cand c = load_cand(cand + i);
     out[atomicAdd(&cursor[c.z], 1)] = c;
   }
 }
@@ -231,7 +232,7 @@ int make_ladder(const double* sigmas_host, int num_sigma, SigmaLadder* out) {
 }
 
 __global__ void keep_all_kernel(const int* __restrict__ n_ptr, int n_max, uint8_t* __restrict__ keep) {
-  const int n = min(*n_ptr, n_max);
+  const int n = min(__ldcg(n_ptr), n_max);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) keep[i] = 1;
 }

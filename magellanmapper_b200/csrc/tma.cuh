@@ -97,6 +97,12 @@ template <int N>
 __device__ __forceinline__ void tma_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
+// the bulk stores of this thread are COMPLETE (written, not merely read from shared
+// memory): required before a CTA exits if a later kernel reads what it stored
+template <int N>
+__device__ __forceinline__ void tma_wait_all() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }

@@ -341,6 +341,7 @@ class Ticket:
     slot: _Slot
     event: "torch.cuda.Event"
     args: tuple                  # everything needed to redo the chunk after an overflow
+    stream: Optional["torch.cuda.Stream"] = None     # the stream the chunk was enqueued on
 
 
 class ChunkDetector:
@@ -400,7 +401,7 @@ class ChunkDetector:
         ev.record()
         slot.busy = True
         return Ticket(slot, ev, (src, sigmas, threshold, overlap, scale, pre, block_shape, z_lo,
-                                 z_hi))
+                                 z_hi), torch.cuda.current_stream())
 
     def collect(self, ticket: Ticket) -> Tuple[np.ndarray, int]:
         """Wait for a chunk; returns ``(survivors as CAND_DTYPE records, number of
@@ -440,9 +441,14 @@ class ChunkDetector:
             need = max(n_peaks, (n_edges - 4096) // 4 + 1)
             self.capacity = max(self.capacity, int(need * 1.25) + 1024)
             self._alloc()
-            return self.collect_device(self.enqueue(*ticket.args))
-        # stream-ordered copy: the slot may be reused by a later chunk right away
-        out = slot.cand[:n_out].clone()
+            with torch.cuda.stream(ticket.stream or torch.cuda.current_stream()):
+                redo = self.enqueue(*ticket.args)
+            return self.collect_device(redo)
+        # copy on the stream the chunk ran on: the slot may then be reused by a later
+        # chunk of that stream right away (consumers on another stream must order
+        # themselves after it)
+        with torch.cuda.stream(ticket.stream or torch.cuda.current_stream()):
+            out = slot.cand[:n_out].clone()
         slot.busy = False
         return out, n_peaks
 
