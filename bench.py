@@ -365,7 +365,7 @@ def main():
     # DRAM traffic of the dominant kernel from the committed ncu capture (bytes per
     # voxel measured on one 505^3 chunk), scaled to this run's average launch size
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic_v7.json")
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic_v10.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
@@ -373,7 +373,7 @@ def main():
             vox_per_launch = units[kinds.index(dom)] / per_kind[dom]["launches"]
             traffic = tj["kernels"][dom]["dram_bytes_per_voxel"] * vox_per_launch
             traffic_src = ("dram__bytes_read.sum + dram__bytes_write.sum per voxel from "
-                           "profiles/r01_traffic_v7.json x this run's voxels per launch")
+                           "profiles/r01_traffic_v10.json x this run's voxels per launch")
     roof = {"bound": "hbm", "kernel": dom, "achieved": per_kind[dom]["gbps"],
             "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": per_kind[dom]["gbps"] / peaks["hbm_gbs"], "traffic": traffic,
