@@ -280,3 +280,22 @@ def test_prune_blobs_mp_index_form_equals_seam_by_seam(monkeypatch):
         if len(df):
             np.testing.assert_allclose(df.to_numpy(), np.array(want_ratios))
     assert len(want) < sum(len(seg[c]) for c in np.ndindex(*seg.shape) if seg[c] is not None)
+
+
+def test_calc_near_intensity_bounds_list_semantics(golden_dir):
+    """importer.calc_near_intensity_bounds (host part, importer.py:1447-1468): one
+    channel APPENDS the extremes to the given lists, several channels REPLACE them by
+    arrays - checked against the reference's outputs for the golden per-plane bounds."""
+    from magellanmapper_b200.io import importer
+    g = np.load(os.path.join(golden_dir, "near_bounds.npz"))
+    lows = [list(r) for r in g["u16_plane_lows"]]
+    highs = [list(r) for r in g["u16_plane_highs"]]
+    mins, maxs = importer.calc_near_intensity_bounds([1.0], [2.0], lows, highs)
+    assert mins[0] == 1.0 and maxs[0] == 2.0 and len(mins) == 2
+    assert mins[1] == g["u16_near_mins"][0] and maxs[1] == g["u16_near_maxs"][0]
+    lows = [list(r) for r in g["u16_2c_plane_lows"]]
+    highs = [list(r) for r in g["u16_2c_plane_highs"]]
+    mins, maxs = importer.calc_near_intensity_bounds([9.0], [9.0], lows, highs)
+    np.testing.assert_array_equal(mins, g["u16_2c_near_mins"])
+    np.testing.assert_array_equal(maxs, g["u16_2c_near_maxs"])
+    assert importer.calc_near_intensity_bounds([3.0], [4.0], [], []) == ([3.0], [4.0])
