@@ -151,6 +151,17 @@ def _gloo_worker(rank, world, port, out_dir):
         whole = np.concatenate([pre.numpy().view(np.uint16), own, suf.numpy().view(np.uint16)])
         np.testing.assert_array_equal(whole, host[w0:w1])
         assert own.base is not None and len(own) == min(w1, held[rank][1]) - max(w0, held[rank][0])
+        # lent units travel as dense sub-boxes (rows of chunk row k restricted to the y
+        # range of chunk column j), pieces from every slab that holds part of the row
+        zb = [(0, 22), (20, 40)]
+        yb = [(0, 2), (1, 3)]
+        loans = [(1, 1, 1, 0), (0, 0, 0, 1)]        # (k, j, owner, worker)
+        boxes = mg._exchange_boxes(vol[held[rank][0]:held[rank][1]].clone(), held, loans, zb, yb,
+                                   None, torch.device("cpu"))
+        mine = {(k, j) for k, j, _, w in loans if w == rank}
+        assert set(boxes) == mine
+        for (k, j), box in boxes.items():
+            assert torch.equal(box, vol[zb[k][0]:zb[k][1], yb[j][0]:yb[j][1]])
         # variable-length gathers (float64 tables and int32 candidate records)
         mine = np.full((3 + 2 * rank, 14), float(rank)) + np.arange(14)
         parts = mg.gather_rows(mine if rank == 0 else mine, 14)
