@@ -28,7 +28,7 @@ constexpr int kLmCols = 120;                   // output columns per warp: 30 la
 
 __device__ __forceinline__ bool row_beats(const float* __restrict__ row, int xl, int x, int xr,
                                           float v) {
-  return fmaxf(fmaxf(__ldg(row + xl), __ldg(row + x)), __ldg(row + xr)) > v;
+  return fmaxf(fmaxf(__ldcg(row + xl), __ldcg(row + x)), __ldcg(row + xr)) > v;
 }
 
 // planes z-1, z+1 of the same scale and all 27 voxels of each adjacent scale
@@ -79,7 +79,7 @@ localmax_kernel(const float* __restrict__ prev, const float* __restrict__ cur,
     const int y = min(max(y0 - 1 + rr, 0), Y - 1);
     v[rr] = make_float4(NEG, NEG, NEG, NEG);
     if (x0 >= 0 && x0 < X)
-      v[rr] = __ldg(reinterpret_cast<const float4*>(plane + (int64_t)y * pitch + x0));
+      v[rr] = __ldcg(reinterpret_cast<const float4*>(plane + (int64_t)y * pitch + x0));
   }
   // columns past X inside a loaded float4 hold row padding: mask them
   if (x0 + 3 >= X) {
@@ -131,7 +131,7 @@ localmax_kernel(const float* __restrict__ prev, const float* __restrict__ cur,
       mask &= mask - 1;
       y = y0 + (bit >> 2);
       x = x0 + (bit & 3);
-      val = __ldg(plane + (int64_t)y * pitch + x);
+      val = __ldcg(plane + (int64_t)y * pitch + x);
       peak = survives_3d_and_scales(prev, cur, next, Z, Y, X, pitch, z, y, x, val);
     }
     const unsigned ballot = __ballot_sync(0xffffffffu, peak);

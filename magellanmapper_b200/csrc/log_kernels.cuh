@@ -66,8 +66,8 @@ conv_strided_kernel(const float* __restrict__ in0, const float* __restrict__ in1
 #pragma unroll
   for (int k = 0; k < NIN; ++k) {
     const int64_t off = s_off[k];
-    const float v0 = __ldg(p0 + off);
-    const float v1 = (MODE == MODE_FIRST) ? 0.f : __ldg(p1 + off);
+    const float v0 = __ldcg(p0 + off);
+    const float v1 = (MODE == MODE_FIRST) ? 0.f : __ldcg(p1 + off);
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
       const int t = k - j;
@@ -438,7 +438,7 @@ conv_x_first_kernel(const float* __restrict__ in, float* __restrict__ outA,
       const int rr = i / WIN, c = i - rr * WIN;
       const int64_t row = r0 + rr;
       float v = 0.f;
-      if (row < nrows) v = __ldg(in + row * pitch + reflect_index(x0 - R + c, X));
+      if (row < nrows) v = __ldcg(in + row * pitch + reflect_index(x0 - R + c, X));
       s[rr * SP + c] = v;
     }
   }

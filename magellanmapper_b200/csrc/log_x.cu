@@ -119,7 +119,7 @@ conv_x_tma_kernel(const __grid_constant__ CUtensorMap tm_in,
         if (src >= 0 && src < G::WIN) {
           v = *reinterpret_cast<const float*>(st_in + x_sw_off(rr, src));
         } else if (r0 + rr < nrows) {                         // volume narrower than the window
-          v = __ldg(in + (r0 + rr) * pitch + (xs + src));
+          v = __ldcg(in + (r0 + rr) * pitch + (xs + src));
         }
         *reinterpret_cast<float*>(st_in + x_sw_off(rr, p)) = v;
       }
@@ -502,7 +502,7 @@ conv_x_warp_kernel(const float* __restrict__ in, float* __restrict__ outA,
         } else {
           const float* src = in + (r0 + rr) * pitch;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) d[k] = __ldg(src + reflect_index(x + k, X));
+          for (int k = 0; k < 4; ++k) d[k] = __ldcg(src + reflect_index(x + k, X));
         }
       }
     }

@@ -179,7 +179,7 @@ z_scan_kernel(int* __restrict__ hist, int Z) {
   const int per = (Z + 1023) / 1024;
   const int lo = threadIdx.x * per, hi = min(Z, lo + per);
   int sum = 0;
-  for (int z = lo; z < hi; ++z) sum += hist[z];
+  for (int z = lo; z < hi; ++z) sum += __ldcg(&hist[z]);
   part[threadIdx.x] = sum;
   __syncthreads();
   for (int d = 1; d < 1024; d <<= 1) {          // Hillis-Steele inclusive scan
@@ -190,7 +190,7 @@ z_scan_kernel(int* __restrict__ hist, int Z) {
   }
   int run = part[threadIdx.x] - sum;             // exclusive prefix of this thread's range
   for (int z = lo; z < hi; ++z) {
-    const int c = hist[z];
+    const int c = __ldcg(&hist[z]);
     hist[z] = run;
     run += c;
   }

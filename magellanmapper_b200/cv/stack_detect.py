@@ -37,11 +37,11 @@ DEVICE_TABLES = True
 #: Chunks with at most this fraction of the largest chunk's voxels run on a side stream
 #: under the kernels of the full chunks (0 = off, the default).  Measured on config 2
 #: with 0.3: 329 -> 319 ms per stack.  OFF because with a device-resident image the two
-#: streams run unsynchronised for a whole stack and the order of a few dozen rows inside
-#: the thin chunks' tables then varies from run to run (same rows; responses of some
-#: candidates differ in the last bits), which breaks the bit-for-bit reproducibility the
-#: tests demand; serialising the streams removes it, routing every workspace read
-#: through L2 and waiting for TMA-store completion do not.  Unresolved: see DESIGN.md.
+#: streams run unsynchronised for a whole stack and the tables of a few thin chunks then
+#: vary from run to run (a handful of rows, occasionally the row count:
+#: tools/side_stream_check.py), which breaks the bit-for-bit reproducibility the tests
+#: demand; serialising the streams removes it, routing every workspace read through L2
+#: and waiting for TMA-store completion do not.  Unresolved: see DESIGN.md.
 THIN_CHUNK_FRACTION = 0.0
 
 
