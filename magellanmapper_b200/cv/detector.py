@@ -125,7 +125,9 @@ class Blobs:
         """Read a ``*_blobs.npz`` archive (detector.py:185-267)."""
         if path is not None:
             self.path = path
-        with np.load(self.path, allow_pickle=True) as archive:
+        # no pickle: keys that would need it (the None-valued metadata saved as object
+        # arrays) are skipped by read_np_archive, as in the reference (np_io.py:159-177)
+        with np.load(self.path) as archive:
             info = np_io.read_np_archive(archive)
         K = self.Keys
         if K.VER.value in info:
@@ -164,7 +166,7 @@ class Blobs:
         else:
             arc = to_add
         if update:
-            with np.load(self.path, allow_pickle=True) as archive:
+            with np.load(self.path) as archive:
                 arc = np_io.read_np_archive(archive)
                 arc.update(to_add)
         libmag.backup_file(self.path)
@@ -324,14 +326,28 @@ def calc_overlap(factor: Optional[int] = None) -> np.ndarray:
 
 
 def sigma_ladder(settings, scaling_factor: float, image_is_f32: bool = False) -> np.ndarray:
-    """The ``blob_log`` scale ladder for a profile: ``linspace(min_sigma_factor,
-    max_sigma_factor, num_sigma) * x-scaling`` (detector.py:903-927).  skimage
-    builds it in the image's float dtype, so a float32 image gets
-    float32-rounded sigmas."""
+    """The ``blob_log`` scale ladder for a profile (detector.py:903-927).
+
+    scikit-image 0.25.2 (``skimage/feature/blob.py``, ``blob_log``) casts the two
+    scalar sigmas to the image's float dtype and builds the ladder as
+    ``np.linspace(0, 1, num_sigma)[:, None] * (max_sigma - min_sigma) + min_sigma``,
+    not as ``np.linspace(min_sigma, max_sigma, num_sigma)``: the two differ in the
+    last bits whenever ``max - min`` is not a power of two (8.9e-16 for 4..10),
+    and the ``radius`` column is ``sigma * sqrt(3)`` of exactly these values.  A
+    float32 image gets float32-rounded ends and a float32 difference."""
     dt = np.float32 if image_is_f32 else np.float64
     lo = np.asarray(settings["min_sigma_factor"] * scaling_factor, dtype=dt)
     hi = np.asarray(settings["max_sigma_factor"] * scaling_factor, dtype=dt)
-    return np.linspace(lo, hi, int(settings["num_sigma"])).astype(np.float64)
+    return skimage_ladder(lo, hi, int(settings["num_sigma"]))
+
+
+def skimage_ladder(lo, hi, num_sigma: int) -> np.ndarray:
+    """``scale * (max_sigma - min_sigma) + min_sigma`` with ``scale =
+    np.linspace(0, 1, num_sigma)`` (float64) and the difference taken in the dtype
+    of ``lo`` / ``hi``, as ``blob_log`` does."""
+    lo, hi = np.asarray(lo), np.asarray(hi)
+    scale = np.linspace(0, 1, int(num_sigma))
+    return (scale * (hi - lo) + lo).astype(np.float64)
 
 
 def input_scale(dtype) -> float:

@@ -282,12 +282,32 @@ class StackDetector(object):
         else:
             thin = set()
 
+        # strips whose chunks are all enqueued but not all collected: a strip's device
+        # buffer may only be handed back to the feeder (which at once starts overwriting
+        # it with strip j + 2) when none of its chunks can still need a redo - a chunk
+        # whose candidate or edge buffer overflowed is re-run from the same device view
+        in_flight = {}                 # strip -> chunks enqueued and not yet collected
+        closed = set()                 # strips with nothing left to enqueue
+
         def finish_oldest():
-            coord, offset, _, _, shape, det_, tickets = pending.popleft()
+            (coord, offset, _, _, shape, det_, tickets), strip = pending.popleft()
             rank_in_grid = int(np.ravel_multi_index(coord, grid))
             for chl, sigmas, ticket in tickets:
                 cand, _ = det_.collect_device(ticket)
                 tables.append(cand, coord, offset, shape[1:3], sigmas, chl, rank_in_grid)
+            if strip is not None:
+                in_flight[strip] -= 1
+                if in_flight[strip] == 0 and strip in closed:
+                    if side is not None:
+                        main.wait_stream(side)          # side-stream readers of the strip
+                    feeder.release(strip)
+
+        def close_strip(strip):
+            closed.add(strip)
+            if in_flight.get(strip, 0) == 0:
+                if side is not None:
+                    main.wait_stream(side)
+                feeder.release(strip)
 
         strip_of, strip_dev = None, None
         for n_done, coord in enumerate(todo):
@@ -298,9 +318,11 @@ class StackDetector(object):
                 j = cols.index(coord[1])
                 if j != strip_of:
                     if strip_of is not None:
-                        if side is not None:
-                            main.wait_stream(side)      # side-stream readers of the old strip
-                        feeder.release(strip_of)
+                        close_strip(strip_of)
+                    # strip j reuses the buffer of strip j - 2: its upload starts when
+                    # the last chunk of that strip has been collected
+                    while feeder.uploaded[j] is None and pending:
+                        finish_oldest()
                     strip_of, strip_dev = j, feeder.strip(j)
                     if side is not None:
                         side.wait_event(feeder.uploaded[j])
@@ -309,23 +331,25 @@ class StackDetector(object):
                 sub = strip_dev[sz, sy.start - y0:sy.stop - y0, sx]
             else:
                 sub = img[sub_roi_slices[coord]]
+            if strip_of is not None:
+                in_flight[strip_of] = in_flight.get(strip_of, 0) + 1
             if coord in thin:
                 if os.environ.get("MMB_SIDE_SERIAL"):
                     side.wait_stream(main)
                 with torch.cuda.stream(side):
-                    pending.append(cls.enqueue_sub_roi(
+                    pending.append((cls.enqueue_sub_roi(
                         coord, sub_rois_offsets[coord], last_coord, denoise_max_shape, None,
-                        sub, channel, False, det=thin_det))
+                        sub, channel, False, det=thin_det), strip_of))
                 if os.environ.get("MMB_SIDE_SERIAL"):
                     main.wait_stream(side)
             else:
-                pending.append(cls.enqueue_sub_roi(
+                pending.append((cls.enqueue_sub_roi(
                     coord, sub_rois_offsets[coord], last_coord, denoise_max_shape, None,
-                    sub, channel, False))
+                    sub, channel, False), strip_of))
         if side is not None:
             main.wait_stream(side)
         if feeder is not None and strip_of is not None:
-            feeder.release(strip_of)
+            close_strip(strip_of)
         while pending:
             finish_oldest()
         if side is not None:

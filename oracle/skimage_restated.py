@@ -52,13 +52,20 @@ def img_as_float(image: np.ndarray) -> np.ndarray:
 
 def sigma_list(min_sigma: float, max_sigma: float, num_sigma: int,
                float_dtype=np.float64) -> np.ndarray:
-    """blob_log's linear scale ladder (``log_scale=False``).  blob_log casts the
-    scalar sigmas to the image's float dtype before ``np.linspace``, so a
-    float32 image gets float32-rounded sigmas; every integer or float64 image
-    (all of MagellanMapper's own call paths) gets float64 ones."""
+    """blob_log's linear scale ladder (``log_scale=False``), as 0.25.2 builds it
+    (``skimage/feature/blob.py``): the scalar sigmas are cast to the image's float
+    dtype (a float32 image gets float32-rounded ends; every integer or float64
+    image - all of MagellanMapper's own call paths - float64 ones) and then
+
+        scale = np.linspace(0, 1, num_sigma)[:, None]
+        sigma_list = scale * (max_sigma - min_sigma) + min_sigma
+
+    which is NOT bit-equal to ``np.linspace(min_sigma, max_sigma, num_sigma)``
+    unless ``max - min`` is a power of two (3..5 is; 4..10 differs by 8.9e-16)."""
     lo = np.asarray(min_sigma, dtype=float_dtype)
     hi = np.asarray(max_sigma, dtype=float_dtype)
-    return np.linspace(lo, hi, int(num_sigma)).astype(np.float64)
+    scale = np.linspace(0, 1, int(num_sigma))
+    return (scale * (hi - lo) + lo).astype(np.float64)
 
 
 def log_cube(image: np.ndarray, sigmas: Sequence[float]) -> np.ndarray:
