@@ -182,9 +182,11 @@ int mmb_detect_chunk(const void* in, int dtype, const int64_t in_strides[3],
 
 /* Asynchronous form: enqueues every kernel of the chunk on `stream` and returns
  * without synchronising; nothing is read back to the host.  `status` is a DEVICE
- * int32[3] written at the end of the chunk: [0] local maxima found (may exceed
+ * int32[4] written at the end of the chunk: [0] local maxima found (may exceed
  * `capacity`), [1] survivors compacted to the front of `cand`, [2] kill edges
- * found by the overlap pruning (may exceed mmb_detect_edge_capacity(capacity)).
+ * found by the overlap pruning (may exceed mmb_detect_edge_capacity(capacity)),
+ * [3] number of candidates whose survival depends on the iteration order of
+ * scikit-image's pair set (at least one killer, none of them a root).
  * The caller copies `status` and `cand[0 .. status[1])` back after the stream
  * reaches this point; if [0] > capacity or [2] > edge capacity the results are
  * incomplete and the chunk must be redone with a larger capacity.  `work` and
@@ -197,6 +199,70 @@ int mmb_detect_chunk_enqueue(const void* in, int dtype, const int64_t in_strides
                              mmb_cand* cand, int capacity, int32_t* status,
                              void* stream);
 int mmb_detect_edge_capacity(int capacity);
+
+/* ---- blob tables of a chunked stack -------------------------------------------------
+ * One detected blob as it leaves a chunk: chunk-local voxel, index into the channel's
+ * sigma ladder, LoG response, linear index of the chunk in the C-ordered chunk grid,
+ * position of the channel in the channel list.  32 bytes.                             */
+typedef struct mmb_row {
+  int32_t z, y, x;
+  int32_t s;
+  float resp;
+  int32_t chunk;
+  int32_t channel;
+  int32_t reserved;
+} mmb_row;
+
+/* Tags the survivors of one chunk (`cand[0 .. n)` of mmb_detect_chunk_enqueue) with
+ * their chunk and channel: the device-side form of Blobs.format_blobs + the chunk
+ * columns chunking.merge_blobs appends (magmap/cv/detector.py:325-364,
+ * magmap/cv/chunking.py:410-445).                                                     */
+int mmb_rows_from_cands(const mmb_cand* cand, int n, int chunk, int channel, mmb_row* out,
+                        void* stream);
+
+/* Appends the candidates `cand[i]` with keep[i] != 0 (all when `keep` is NULL) that lie,
+ * after adding `shift` (z, y, x), inside the box [lo, hi) to `dst` at *counter (a DEVICE
+ * int32 that keeps counting past `capacity`, so overflow is detectable).  The seamless
+ * multi-GPU mode uses it to turn tile-local local maxima into the owned part of the
+ * global candidate list, and to list the survivors of the single global _prune_blobs
+ * (no reference counterpart: the reference has one process-local list, detector.py:931). */
+int mmb_cands_append(const mmb_cand* cand, int n, const uint8_t* keep, const int32_t shift[3],
+                     const int32_t lo[3], const int32_t hi[3], mmb_cand* dst, int capacity,
+                     int32_t* counter, void* stream);
+
+/* Chunk-grid geometry (chunking.stack_splitter, stack_detect.setup_blocks): HOST
+ * pointers, read before the call returns.                                            */
+typedef struct mmb_stack_geom {
+  int32_t grid[3];           /* chunks per axis (z, y, x), each <= 128                  */
+  int32_t overlap[3];        /* Blocks.overlap                                          */
+  int32_t tol[3];            /* Blocks.tol (inclusive box tolerance, < 64)              */
+  int32_t pad[3];            /* Blocks.overlap_padding                                  */
+  const int32_t* start[3];   /* start[a][j]: first voxel of chunk section j on axis a  */
+  const int32_t* size[3];    /* size[a][j]: its extent                                  */
+  int32_t n_channels;        /* channels detected in this pass                          */
+  int32_t num_sigma;         /* row pitch of `sigmas`                                   */
+  const double* sigmas;      /* [n_channels][num_sigma] sigma ladders                   */
+  const int32_t* channel_ids;/* [n_channels] value of the table's channel column       */
+} mmb_stack_geom;
+
+/* Replaces chunking.merge_blobs -> StackPruner.prune_blobs_mp (prune_overlap,
+ * detector.remove_close_blobs) -> the final column layout of detect_blobs_blocks
+ * (magmap/cv/stack_detect.py:680-861, :644-677, :455-467; detector.py:1009-1085) on
+ * the rows of every chunk, in any order: rows are put into merge order (chunks in grid
+ * order, channels in request order, peak_local_max order inside a detection), seams
+ * are pruned axis by axis exactly as the reference walks them, and the float64 table is
+ * written to `out_table` (capacity n rows): 8 columns z, y, x, radius, confirmed,
+ * truth, channel, region when `final_layout`, else the 11 Blobs.Cols columns.
+ * *n_out (DEVICE int32) = rows written.  seam_counts (DEVICE, may be NULL):
+ * [n_channels][3][128][4] int32 = per channel, axis and seam {rows in the slab, rows
+ * after pruning, rows in the ratio region, matched checks} for
+ * detector.meas_pruning_ratio.  Asynchronous on `stream`; `work` holds
+ * mmb_stack_tables_work_bytes(n) bytes.  A grid of one chunk just orders the rows
+ * (peak_local_max order) and formats them.                                           */
+int64_t mmb_stack_tables_work_bytes(int n_rows);
+int mmb_stack_tables(const mmb_row* rows, int n, const mmb_stack_geom* geom, int final_layout,
+                     double* out_table, int32_t* n_out, int32_t* seam_counts, void* work,
+                     void* stream);
 
 /* number of kernels this library has launched in this process (bench.py's
  * gpu_launches).                                                              */

@@ -30,6 +30,20 @@ class MmbPreprocParams(C.Structure):
                 ("erosion_threshold", C.c_double)]
 
 
+class MmbRow(C.Structure):
+    _fields_ = [("z", C.c_int32), ("y", C.c_int32), ("x", C.c_int32), ("s", C.c_int32),
+                ("resp", C.c_float), ("chunk", C.c_int32), ("channel", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class MmbStackGeom(C.Structure):
+    _fields_ = [("grid", C.c_int32 * 3), ("overlap", C.c_int32 * 3), ("tol", C.c_int32 * 3),
+                ("pad", C.c_int32 * 3), ("start", C.POINTER(C.c_int32) * 3),
+                ("size", C.POINTER(C.c_int32) * 3), ("n_channels", C.c_int32),
+                ("num_sigma", C.c_int32), ("sigmas", C.POINTER(C.c_double)),
+                ("channel_ids", C.POINTER(C.c_int32))]
+
+
 class MmbError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"mmb200 error {code}: {msg}")
@@ -74,6 +88,12 @@ SIGNATURES = {
     "mmb_prune_within_zsorted": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.c_int,
                                            C.c_double, C.c_int, C.c_int, _vp, _vp]),
     "mmb_prune_seams": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _I32x3, _vp, _vp, _vp]),
+    "mmb_rows_from_cands": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "mmb_cands_append": (C.c_int, [_vp, C.c_int, _vp, _I32x3, _I32x3, _I32x3, _vp, C.c_int, _vp,
+                                   _vp]),
+    "mmb_stack_tables_work_bytes": (C.c_int64, [C.c_int]),
+    "mmb_stack_tables": (C.c_int, [_vp, C.c_int, C.POINTER(MmbStackGeom), C.c_int, _vp, _vp, _vp,
+                                   _vp, _vp]),
     "mmb_detect_work_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int64, C.c_int]),
     "mmb_detect_edge_capacity": (C.c_int, [C.c_int]),
     "mmb_detect_chunk_enqueue": (C.c_int, [_vp, C.c_int, _I64x3, C.c_int, C.c_int, C.c_int,
@@ -86,6 +106,12 @@ SIGNATURES = {
                                    C.c_int, C.POINTER(C.c_double), C.c_int, C.c_double,
                                    C.c_double, C.c_int, C.c_int, _vp, _vp, C.c_int,
                                    C.POINTER(C.c_int), C.POINTER(C.c_int), _vp]),
+}
+
+#: bench / test utilities of include/mmb200_tools.h (not the reference-facing boundary)
+TOOLS_SIGNATURES = {
+    "mmb_synth_nuclei": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64,
+                                   C.c_int64, C.c_uint64, C.c_double, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None
@@ -101,7 +127,7 @@ def load() -> C.CDLL:
             f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; "
             f"g.build()'` (there is no CPU fallback)")
     lib = C.CDLL(LIB_PATH)
-    for name, (res, args) in SIGNATURES.items():
+    for name, (res, args) in list(SIGNATURES.items()) + list(TOOLS_SIGNATURES.items()):
         fn = getattr(lib, name)          # AttributeError if the symbol is absent
         fn.restype = res
         fn.argtypes = args

@@ -115,13 +115,16 @@ int localmax_impl(const float* prev, const float* cur, const float* next, int Z,
 int prune_within_impl(const mmb_cand* cand, int n, const double* sigmas_host, int num_sigma,
                       double overlap, int Y, int X, uint8_t* keep, cudaStream_t st, int z_sorted);
 int make_ladder(const double* sigmas_host, int num_sigma, SigmaLadder* out);
+CellGrid make_cell_grid(int Z, int Y, int X, int min_edge, int64_t max_cells);
+int64_t cell_count(const CellGrid& g);
+int prune_cell_edge(const SigmaLadder& ladder);
 int prune_within_enqueue(const mmb_cand* cand, const int* n_ptr, int n_max,
                          const SigmaLadder& ladder, double overlap, int Y, int X, int2* edges,
                          int edge_cap, int* edge_count, unsigned char* state, uint8_t* keep,
-                         cudaStream_t st, int z_sorted);
-
-int sort_by_z_enqueue(const mmb_cand* cand, const int* n_ptr, int n_max, int Z, int* hist,
-                      mmb_cand* out, cudaStream_t st);
+                         cudaStream_t st, const CellGrid& grid, const int* cell_end,
+                         int* od_count);
+int sort_by_cell_enqueue(const mmb_cand* cand, const int* n_ptr, int n_max, const CellGrid& grid,
+                         int* hist, mmb_cand* out, cudaStream_t st);
 
 // stable stream compaction of the survivors to the front of a second buffer
 __global__ void compact_kernel(const mmb_cand* __restrict__ in, const uint8_t* __restrict__ keep,
@@ -185,7 +188,8 @@ static ChunkLayout chunk_layout(int Z, int Y, int64_t pitch, int capacity) {
   ChunkLayout L;
   L.vol_b = align256((int64_t)Z * Y * pitch * (int64_t)sizeof(float));
   L.cand_b = align256((int64_t)capacity * (int64_t)sizeof(mmb_cand));
-  L.zhist_b = align256((int64_t)Z * (int64_t)sizeof(int));
+  // cell histogram of the pair search: cells are never narrower than 8 voxels
+  L.zhist_b = align256((cdiv(Z, 8) * cdiv(Y, 8) * cdiv(pitch, 8) + 1) * (int64_t)sizeof(int));
   L.keep_b = align256(capacity);
   L.edge_cap = 4 * capacity + 4096;
   L.edges_b = align256((int64_t)L.edge_cap * (int64_t)sizeof(int2));
@@ -199,7 +203,8 @@ extern "C" int64_t mmb_detect_work_bytes(int Z, int Y, int64_t pitch, int capaci
 }
 
 // status (device int32[4]): [0] local maxima found (may exceed capacity), [1] survivors
-// written to `cand`, [2] kill edges found (may exceed mmb_detect_edge_capacity(capacity))
+// written to `cand`, [2] kill edges found (may exceed mmb_detect_edge_capacity(capacity)),
+// [3] size of the set whose survival depends on scikit-image's pair iteration order
 extern "C" int mmb_detect_chunk_enqueue(const void* in, int dtype, const int64_t in_strides[3],
                                         int Z, int Y, int X, int64_t pitch, double scale,
                                         const mmb_preproc_params* pre, int bz, int by, int bx,
@@ -229,13 +234,13 @@ extern "C" int mmb_detect_chunk_enqueue(const void* in, int dtype, const int64_t
   uint8_t* keep = (uint8_t*)tail;                       tail += L.keep_b;
   int2* edges = (int2*)tail;                            tail += L.edges_b;
   unsigned char* state = (unsigned char*)tail;          tail += L.state_b;
-  int* counters = (int*)tail;      // [0] peaks, [1] survivors, [2] edges
+  int* counters = (int*)tail;      // [0] peaks, [1] survivors, [2] edges, [3] order-dependent set
 
   if (pre) rc = preprocess_impl(in, dtype, in_strides, Z, Y, X, bz, by, bx, pre, F, pitch, st);
   else rc = to_float_impl(in, dtype, in_strides, Z, Y, X, F, pitch, scale, st);
   if (rc) return rc;
 
-  MMB_CHECK_CUDA(cudaMemsetAsync(counters, 0, 3 * sizeof(int), st));
+  MMB_CHECK_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(int), st));
   const float thr = (float)threshold;
   // ring slot of scale i is i % 3; local maxima of scale i-1 run once scale i exists
   for (int i = 0; i < num_sigma; ++i) {
@@ -255,15 +260,17 @@ extern "C" int mmb_detect_chunk_enqueue(const void* in, int dtype, const int64_t
                        capacity, counters, st);
     if (rc) return rc;
   }
-  // list the local maxima by plane so that the pair search of the pruning stops at
-  // the cut-off distance in z instead of visiting every pair
+  // list the local maxima cell by cell (cells as wide as the pruning cut-off) so that
+  // the pair search visits the 27 cells around a candidate instead of every pair
+  const int cell_edge = prune_cell_edge(ladder) < 8 ? 8 : prune_cell_edge(ladder);
+  const CellGrid cgrid = make_cell_grid(Z, Y, X, cell_edge, L.zhist_b / (int64_t)sizeof(int) - 1);
   {
     ProfScope ps(PROF_COMPACT, capacity, st);
-    rc = sort_by_z_enqueue(cand2, counters, capacity, Z, zhist, cand3, st);
+    rc = sort_by_cell_enqueue(cand2, counters, capacity, cgrid, zhist, cand3, st);
     if (rc) return rc;
   }
   rc = prune_within_enqueue(cand3, counters, capacity, ladder, overlap, Y, X, edges, L.edge_cap,
-                            counters + 2, state, keep, st, 1);
+                            counters + 2, state, keep, st, cgrid, zhist, counters + 3);
   if (rc) return rc;
   {
     ProfScope ps(PROF_COMPACT, capacity, st);
@@ -271,7 +278,7 @@ extern "C" int mmb_detect_chunk_enqueue(const void* in, int dtype, const int64_t
                                                                   cand, counters + 1);
   }
   MMB_CHECK_LAUNCH();
-  MMB_CHECK_CUDA(cudaMemcpyAsync(status, counters, 3 * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  MMB_CHECK_CUDA(cudaMemcpyAsync(status, counters, 4 * sizeof(int), cudaMemcpyDeviceToDevice, st));
   return MMB_OK;
 }
 

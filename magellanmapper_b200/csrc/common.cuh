@@ -83,6 +83,13 @@ struct SigmaLadder {
   int n;
 };
 
+// Cell grid of the pruning pair search (prune.cu): cubic cells of `cs` voxels, numbered
+// z, y, x-major.
+struct CellGrid {
+  int cs;              // cell edge in voxels, >= the pair cut-off distance
+  int ncz, ncy, ncx;
+};
+
 int num_sms();   // SM count of the current device (cached)
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -53,13 +53,21 @@ __device__ double overlap_f64(const mmb_cand& a, const mmb_cand& b, double s1, d
 
 constexpr int kTile = 256;
 
-// all pairs i < j, tile of j staged in shared memory; emits (killer, victim)
+// Cell grid for the pair search: candidates are listed cell by cell (counting sort,
+// below) with cubic cells at least as wide as the cut-off distance, so every partner of
+// a candidate lies in the 27 cells around its own; cells are numbered z, y, x-major,
+// which makes the three x-neighbours of a (z, y) cell row one contiguous range.
+__host__ __device__ __forceinline__ int cell_of(const CellGrid& g, int z, int y, int x) {
+  return ((z / g.cs) * g.ncy + y / g.cs) * g.ncx + x / g.cs;
+}
+
+// pairs i < j (positions in the cell-sorted list) closer than the cut-off; emits
+// (killer, victim).  cell_end[c] = one past the last candidate of cell c.
 __global__ void __launch_bounds__(kTile)
 prune_edges_kernel(const mmb_cand* __restrict__ cand, const int* __restrict__ n_ptr, int n_max,
                    const __grid_constant__ SigmaLadder ladder, double overlap, int Y, int X,
                    int2* __restrict__ edges, int edge_cap, int* __restrict__ edge_count,
-                   int z_sorted) {
-  __shared__ mmb_cand tile[kTile];
+                   const __grid_constant__ CellGrid grid, const int* __restrict__ cell_end) {
   __shared__ double sigmas[kMaxSigmas];
   // the candidate count lives on the device (no host round trip); the grid is
   // sized for the buffer capacity and surplus CTAs leave at once
@@ -69,50 +77,46 @@ prune_edges_kernel(const mmb_cand* __restrict__ cand, const int* __restrict__ n_
   for (int k = threadIdx.x; k < num_sigma; k += kTile) sigmas[k] = ladder.s[k];
   __syncthreads();
   const int i = blockIdx.x * kTile + threadIdx.x;
-  mmb_cand me;
-  me.z = me.y = me.x = 0; me.s = 0; me.resp = 0.f;
-  double my_sigma = 0.0;
-  if (i < n) { me = load_cand(cand + i); my_sigma = sigmas[me.s]; }
+  if (i >= n) return;
+  const mmb_cand me = load_cand(cand + i);
+  const double my_sigma = sigmas[me.s];
   const double smax = sigmas[num_sigma - 1] > sigmas[0] ? sigmas[num_sigma - 1] : sigmas[0];
   // spheres can only touch when |d| <= (s1+s2)*sqrt(3) <= 2*smax*sqrt(3)
   const float cut = (float)(2.0 * smax * 1.7320508075688772) + 1.0f;
   const float cut2 = cut * cut;
-  // candidates listed by ascending z (the global prune of the seamless mode): once
-  // a tile starts farther above this block's last candidate than the cut-off, so
-  // does every later tile
-  const int z_block_max =
-      z_sorted ? __ldcg(&cand[min(n, (int)(blockIdx.x + 1) * kTile) - 1].z) : 0;
-  // tiles with j > i only: start at this block's own tile
-  for (int j0 = blockIdx.x * kTile; j0 < n; j0 += kTile) {
-    __syncthreads();
-    const int jl = j0 + threadIdx.x;
-    if (jl < n) tile[threadIdx.x] = load_cand(cand + jl);
-    __syncthreads();
-    if (z_sorted && (float)(tile[0].z - z_block_max) > cut) break;      // block-uniform
-    if (i >= n) continue;
-    const int cnt = n - j0 < kTile ? n - j0 : kTile;
-    for (int t = 0; t < cnt; ++t) {
-      const int j = j0 + t;
-      if (j <= i) continue;
-      const mmb_cand o = tile[t];
-      const float dz = (float)(o.z - me.z);
-      if (fabsf(dz) > cut) continue;
-      const float dy = (float)(o.y - me.y), dx = (float)(o.x - me.x);
-      if (dz * dz + dy * dy + dx * dx > cut2) continue;
-      const double so = sigmas[o.s];
-      if (overlap_f64(me, o, my_sigma, so) > overlap) {
-        int killer, victim;
-        if (my_sigma > so) { killer = i; victim = j; }
-        else if (so > my_sigma) { killer = j; victim = i; }
-        else {
-          const long long li = (((long long)me.z * Y + me.y) * X + me.x) * num_sigma + me.s;
-          const long long lj = (((long long)o.z * Y + o.y) * X + o.x) * num_sigma + o.s;
-          // equal sigma: the blob listed first by peak_local_max is removed
-          if (listed_first(me.resp, li, o.resp, lj)) { victim = i; killer = j; }
-          else { victim = j; killer = i; }
+  const int cz = me.z / grid.cs, cy = me.y / grid.cs, cx = me.x / grid.cs;
+  const int x_lo = max(cx - 1, 0), x_hi = min(cx + 1, grid.ncx - 1);
+  for (int dz = -1; dz <= 1; ++dz) {
+    const int zz = cz + dz;
+    if (zz < 0 || zz >= grid.ncz) continue;
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int yy = cy + dy;
+      if (yy < 0 || yy >= grid.ncy) continue;
+      const int c_first = (zz * grid.ncy + yy) * grid.ncx + x_lo;
+      const int c_last = c_first + (x_hi - x_lo);
+      int j = c_first > 0 ? __ldcg(cell_end + c_first - 1) : 0;
+      const int j_end = __ldcg(cell_end + c_last);
+      if (j <= i) j = i + 1;                        // pairs are emitted once, by the lower index
+      for (; j < j_end; ++j) {
+        const mmb_cand o = load_cand(cand + j);
+        const float dzf = (float)(o.z - me.z);
+        const float dyf = (float)(o.y - me.y), dxf = (float)(o.x - me.x);
+        if (dzf * dzf + dyf * dyf + dxf * dxf > cut2) continue;
+        const double so = sigmas[o.s];
+        if (overlap_f64(me, o, my_sigma, so) > overlap) {
+          int killer, victim;
+          if (my_sigma > so) { killer = i; victim = j; }
+          else if (so > my_sigma) { killer = j; victim = i; }
+          else {
+            const long long li = (((long long)me.z * Y + me.y) * X + me.x) * num_sigma + me.s;
+            const long long lj = (((long long)o.z * Y + o.y) * X + o.x) * num_sigma + o.s;
+            // equal sigma: the blob listed first by peak_local_max is removed
+            if (listed_first(me.resp, li, o.resp, lj)) { victim = i; killer = j; }
+            else { victim = j; killer = i; }
+          }
+          const int e = atomicAdd(edge_count, 1);
+          if (e < edge_cap) edges[e] = make_int2(killer, victim);
         }
-        const int e = atomicAdd(edge_count, 1);
-        if (e < edge_cap) edges[e] = make_int2(killer, victim);
       }
     }
   }
@@ -123,7 +127,7 @@ __global__ void __launch_bounds__(1024)
 prune_resolve_kernel(const int* __restrict__ n_ptr, int n_max, const int2* __restrict__ edges,
                      const int* __restrict__ n_edges_ptr, int edge_cap,
                      unsigned char* __restrict__ state, unsigned char* __restrict__ mark,
-                     unsigned char* __restrict__ keep) {
+                     unsigned char* __restrict__ keep, int* __restrict__ od_count) {
   __shared__ int remaining;
   const int n = min(__ldcg(n_ptr), n_max);
   const int n_edges = min(__ldcg(n_edges_ptr), edge_cap);
@@ -158,26 +162,50 @@ prune_resolve_kernel(const int* __restrict__ n_ptr, int n_max, const int2* __res
     if (r == 0) break;
   }
   for (int v = threadIdx.x; v < n; v += blockDim.x) keep[v] = state[v] == 1 ? 1 : 0;
+  // size of the set whose fate depends on scikit-image's pair iteration order: blobs
+  // with at least one killer, none of which is a root (a blob nobody kills).  mark
+  // bit 0 = has a killer, bit 1 = killed by a root.
+  if (od_count) {
+    __syncthreads();
+    for (int v = threadIdx.x; v < n; v += blockDim.x) mark[v] = 0;
+    __syncthreads();
+    for (int e = threadIdx.x; e < n_edges; e += blockDim.x) {
+      const int2 kv = __ldcg(&edges[e]);
+      atomicOr((unsigned int*)(mark + (kv.y & ~3)), 1u << (8 * (kv.y & 3)));
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < n_edges; e += blockDim.x) {
+      const int2 kv = __ldcg(&edges[e]);
+      if (!(mark[kv.x] & 1)) atomicOr((unsigned int*)(mark + (kv.y & ~3)), 2u << (8 * (kv.y & 3)));
+    }
+    __syncthreads();
+    int mine = 0;
+    for (int v = threadIdx.x; v < n; v += blockDim.x) mine += (mark[v] & 3) == 1 ? 1 : 0;
+    if (mine) atomicAdd(od_count, mine);
+  }
 }
 
-// ---- counting sort of the candidates by z plane -------------------------------------
-// The pair search only has to look 2*sigma_max*sqrt(3)+1 planes up once the
-// candidates are listed by ascending z (prune_edges_kernel's z_sorted path); local
-// maxima arrive in atomic order, so they are bucketed by plane first: histogram,
-// single-CTA exclusive scan, scatter.  The order inside a plane is arbitrary - the
-// kill-graph resolution does not depend on the listing order.
-__global__ void z_hist_kernel(const mmb_cand* __restrict__ cand, const int* __restrict__ n_ptr,
-                              int n_max, int* __restrict__ hist) {
+// ---- counting sort of the candidates by cell -----------------------------------------
+// Local maxima arrive in atomic order; the pair search wants them cell by cell
+// (CellGrid above): histogram, single-CTA exclusive scan, scatter.  The order inside a
+// cell is arbitrary - the kill-graph resolution does not depend on the listing order.
+// After the scatter hist[c] = one past the last candidate of cell c.
+__global__ void cell_hist_kernel(const mmb_cand* __restrict__ cand, const int* __restrict__ n_ptr,
+                                 int n_max, const __grid_constant__ CellGrid grid,
+                                 int* __restrict__ hist) {
   const int n = min(__ldcg(n_ptr), n_max);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) atomicAdd(&hist[__ldcg(&cand[i].z)], 1);
+  if (i < n) {
+    const mmb_cand c = load_cand(cand + i);
+    atomicAdd(&hist[cell_of(grid, c.z, c.y, c.x)], 1);
+  }
 }
 
 __global__ void __launch_bounds__(1024)
-z_scan_kernel(int* __restrict__ hist, int Z) {
+cell_scan_kernel(int* __restrict__ hist, int ncells) {
   __shared__ int part[1024];
-  const int per = (Z + 1023) / 1024;
-  const int lo = threadIdx.x * per, hi = min(Z, lo + per);
+  const int per = (ncells + 1023) / 1024;
+  const int lo = min(ncells, (int)threadIdx.x * per), hi = min(ncells, lo + per);
   int sum = 0;
   for (int z = lo; z < hi; ++z) sum += __ldcg(&hist[z]);
   part[threadIdx.x] = sum;
@@ -196,29 +224,53 @@ z_scan_kernel(int* __restrict__ hist, int Z) {
   }
 }
 
-__global__ void z_scatter_kernel(const mmb_cand* __restrict__ cand, const int* __restrict__ n_ptr,
-                                 int n_max, int* __restrict__ cursor,
-                                 mmb_cand* __restrict__ out) {
+__global__ void cell_scatter_kernel(const mmb_cand* __restrict__ cand,
+                                    const int* __restrict__ n_ptr, int n_max,
+                                    const __grid_constant__ CellGrid grid,
+                                    int* __restrict__ cursor, mmb_cand* __restrict__ out) {
   const int n = min(__ldcg(n_ptr), n_max);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     const mmb_cand c = load_cand(cand + i);
-    out[atomicAdd(&cursor[c.z], 1)] = c;
+    out[atomicAdd(&cursor[cell_of(grid, c.z, c.y, c.x)], 1)] = c;
   }
 }
 
-// cand[0 .. min(*n_ptr, n_max)) -> out, listed by ascending z; hist = Z ints of scratch
-int sort_by_z_enqueue(const mmb_cand* cand, const int* n_ptr, int n_max, int Z, int* hist,
-                      mmb_cand* out, cudaStream_t st) {
+// cells at least `min_edge` voxels wide over a (Z, Y, X) volume; the edge grows until
+// the grid fits `max_cells` (the caller's scratch)
+CellGrid make_cell_grid(int Z, int Y, int X, int min_edge, int64_t max_cells) {
+  CellGrid g;
+  g.cs = min_edge < 1 ? 1 : min_edge;
+  for (;;) {
+    g.ncz = (int)cdiv(Z, g.cs); g.ncy = (int)cdiv(Y, g.cs); g.ncx = (int)cdiv(X, g.cs);
+    if ((int64_t)g.ncz * g.ncy * g.ncx <= max_cells) break;
+    g.cs += (g.cs + 3) / 4;
+  }
+  return g;
+}
+int64_t cell_count(const CellGrid& g) { return (int64_t)g.ncz * g.ncy * g.ncx; }
+
+// cand[0 .. min(*n_ptr, n_max)) -> out, listed cell by cell; hist = cell_count ints
+int sort_by_cell_enqueue(const mmb_cand* cand, const int* n_ptr, int n_max, const CellGrid& grid,
+                         int* hist, mmb_cand* out, cudaStream_t st) {
   if (n_max <= 0) return MMB_OK;
-  MMB_CHECK_CUDA(cudaMemsetAsync(hist, 0, (size_t)Z * sizeof(int), st));
-  z_hist_kernel<<<(unsigned)cdiv(n_max, 256), 256, 0, st>>>(cand, n_ptr, n_max, hist);
+  const int ncells = (int)cell_count(grid);
+  MMB_CHECK_CUDA(cudaMemsetAsync(hist, 0, (size_t)ncells * sizeof(int), st));
+  cell_hist_kernel<<<(unsigned)cdiv(n_max, 256), 256, 0, st>>>(cand, n_ptr, n_max, grid, hist);
   MMB_CHECK_LAUNCH();
-  z_scan_kernel<<<1, 1024, 0, st>>>(hist, Z);
+  cell_scan_kernel<<<1, 1024, 0, st>>>(hist, ncells);
   MMB_CHECK_LAUNCH();
-  z_scatter_kernel<<<(unsigned)cdiv(n_max, 256), 256, 0, st>>>(cand, n_ptr, n_max, hist, out);
+  cell_scatter_kernel<<<(unsigned)cdiv(n_max, 256), 256, 0, st>>>(cand, n_ptr, n_max, grid, hist,
+                                                                  out);
   MMB_CHECK_LAUNCH();
   return MMB_OK;
+}
+
+// cell edge that covers the pair cut-off 2 * sigma_max * sqrt(3) + 1 of a ladder
+int prune_cell_edge(const SigmaLadder& ladder) {
+  double smax = 0.0;
+  for (int k = 0; k < ladder.n; ++k) smax = ladder.s[k] > smax ? ladder.s[k] : smax;
+  return (int)ceil(2.0 * smax * 1.7320508075688772 + 1.0) + 1;
 }
 
 int make_ladder(const double* sigmas_host, int num_sigma, SigmaLadder* out) {
@@ -231,19 +283,29 @@ int make_ladder(const double* sigmas_host, int num_sigma, SigmaLadder* out) {
   return MMB_OK;
 }
 
+__global__ void max_z_kernel(const mmb_cand* __restrict__ cand, int n, int* __restrict__ zmax) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int z = i < n ? __ldcg(&cand[i].z) : 0;
+  z = __reduce_max_sync(0xffffffffu, z);
+  if ((threadIdx.x & 31) == 0 && z > 0) atomicMax(zmax, z);
+}
+
 __global__ void keep_all_kernel(const int* __restrict__ n_ptr, int n_max, uint8_t* __restrict__ keep) {
   const int n = min(__ldcg(n_ptr), n_max);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) keep[i] = 1;
 }
 
-// Fully asynchronous pruning of the first min(*n_ptr, n_max) candidates.  Scratch is
-// caller-provided: edges[edge_cap], edge_count (1 int), state[2 * (n_max + 8)] bytes.
-// *edge_count may exceed edge_cap afterwards: the caller must check and redo.
+// Fully asynchronous pruning of the first min(*n_ptr, n_max) candidates, which must be
+// listed cell by cell (sort_by_cell_enqueue with `grid`, cell_end = its histogram).
+// Scratch is caller-provided: edges[edge_cap], edge_count (1 int), state[2 * (n_max + 8)]
+// bytes.  *edge_count may exceed edge_cap afterwards: the caller must check and redo.
+// od_count (may be NULL): incremented by the size of the order-dependent set.
 int prune_within_enqueue(const mmb_cand* cand, const int* n_ptr, int n_max,
                          const SigmaLadder& ladder, double overlap, int Y, int X, int2* edges,
                          int edge_cap, int* edge_count, unsigned char* state, uint8_t* keep,
-                         cudaStream_t st, int z_sorted) {
+                         cudaStream_t st, const CellGrid& grid, const int* cell_end,
+                         int* od_count) {
   if (n_max <= 0) return MMB_OK;
   const int64_t npad = (n_max + 3) / 4 * 4 + 4;
   MMB_CHECK_CUDA(cudaMemsetAsync(edge_count, 0, sizeof(int), st));
@@ -257,37 +319,88 @@ int prune_within_enqueue(const mmb_cand* cand, const int* n_ptr, int n_max,
   {
     ProfScope ps(PROF_PRUNE_EDGES, n_max, st);
     prune_edges_kernel<<<(unsigned)cdiv(n_max, kTile), kTile, 0, st>>>(
-        cand, n_ptr, n_max, ladder, overlap, Y, X, edges, edge_cap, edge_count, z_sorted);
+        cand, n_ptr, n_max, ladder, overlap, Y, X, edges, edge_cap, edge_count, grid, cell_end);
   }
   MMB_CHECK_LAUNCH();
   {
     ProfScope ps(PROF_PRUNE_RESOLVE, n_max, st);
     prune_resolve_kernel<<<1, 1024, 0, st>>>(n_ptr, n_max, edges, edge_count, edge_cap, state,
-                                             state + npad, keep);
+                                             state + npad, keep, od_count);
   }
   MMB_CHECK_LAUNCH();
   return MMB_OK;
 }
 
+// keep flags refer to the CALLER's order: the candidates are bucketed into a scratch
+// copy and pruned there; the scatter records where every candidate went, and each
+// original candidate then looks its own flag up by that position.
+__global__ void cell_scatter_track_kernel(const mmb_cand* __restrict__ cand, int n,
+                                          const __grid_constant__ CellGrid grid,
+                                          int* __restrict__ cursor, mmb_cand* __restrict__ out,
+                                          int* __restrict__ where) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const mmb_cand c = load_cand(cand + i);
+    const int at = atomicAdd(&cursor[cell_of(grid, c.z, c.y, c.x)], 1);
+    out[at] = c;
+    where[i] = at;
+  }
+}
+__global__ void gather_keep_kernel(const uint8_t* __restrict__ keep_sorted,
+                                   const int* __restrict__ where, int n,
+                                   uint8_t* __restrict__ keep) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keep[i] = keep_sorted[where[i]];
+}
+
 int prune_within_impl(const mmb_cand* cand, int n, const double* sigmas_host, int num_sigma,
                       double overlap, int Y, int X, uint8_t* keep, cudaStream_t st, int z_sorted) {
+  (void)z_sorted;       // any listing order is accepted: candidates are bucketed here
   if (n == 0) return MMB_OK;
   SigmaLadder ladder;
   int rc = make_ladder(sigmas_host, num_sigma, &ladder);
   if (rc) return rc;
-  int* d_counts = nullptr;          // [0] = n, [1] = edge count
+  // the ABI passes Y and X only: the z extent of the coordinates is found on the device
+  int* d_counts = nullptr;          // [0] = n, [1] = edge count, [2] = max z
   int2* d_edges = nullptr;
   unsigned char* d_state = nullptr;
+  mmb_cand* d_sorted = nullptr;
+  int* d_where = nullptr;
+  int* d_cells = nullptr;
+  uint8_t* d_keep = nullptr;
   const int64_t npad = (n + 3) / 4 * 4 + 4;
-  MMB_CHECK_CUDA(cudaMallocAsync((void**)&d_counts, 2 * sizeof(int), st));
-  MMB_CHECK_CUDA(cudaMallocAsync((void**)&d_state, 2 * npad, st));
+  MMB_CHECK_CUDA(cudaMallocAsync((void**)&d_counts, 4 * sizeof(int), st));
+  MMB_CHECK_CUDA(cudaMemsetAsync(d_counts, 0, 4 * sizeof(int), st));
   MMB_CHECK_CUDA(cudaMemcpyAsync(d_counts, &n, sizeof(int), cudaMemcpyHostToDevice, st));
-  int edge_cap = 4 * n + 4096;
+  max_z_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(cand, n, d_counts + 2);
+  MMB_CHECK_LAUNCH();
+  int zmax = 0;
+  MMB_CHECK_CUDA(cudaMemcpyAsync(&zmax, d_counts + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MMB_CHECK_CUDA(cudaStreamSynchronize(st));
+  const CellGrid grid = make_cell_grid(zmax + 1, Y, X, prune_cell_edge(ladder),
+                                       (int64_t)1 << 26);
+  const int64_t ncells = cell_count(grid);
+  MMB_CHECK_CUDA(cudaMallocAsync((void**)&d_state, 2 * npad, st));
+  MMB_CHECK_CUDA(cudaMallocAsync((void**)&d_sorted, (size_t)n * sizeof(mmb_cand), st));
+  MMB_CHECK_CUDA(cudaMallocAsync((void**)&d_where, (size_t)n * sizeof(int), st));
+  MMB_CHECK_CUDA(cudaMallocAsync((void**)&d_keep, (size_t)n, st));
+  MMB_CHECK_CUDA(cudaMallocAsync((void**)&d_cells, (size_t)ncells * sizeof(int), st));
+  MMB_CHECK_CUDA(cudaMemsetAsync(d_cells, 0, (size_t)ncells * sizeof(int), st));
+  cell_hist_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(cand, d_counts, n, grid, d_cells);
+  MMB_CHECK_LAUNCH();
+  cell_scan_kernel<<<1, 1024, 0, st>>>(d_cells, (int)ncells);
+  MMB_CHECK_LAUNCH();
+  cell_scatter_track_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(cand, n, grid, d_cells,
+                                                                    d_sorted, d_where);
+  MMB_CHECK_LAUNCH();
+  int64_t edge_cap = 4 * (int64_t)n + 4096;
+  if (edge_cap > 0x7fffffff) edge_cap = 0x7fffffff;
   int n_edges = 0;
   for (int attempt = 0; attempt < 2; ++attempt) {
     MMB_CHECK_CUDA(cudaMallocAsync((void**)&d_edges, (size_t)edge_cap * sizeof(int2), st));
-    rc = prune_within_enqueue(cand, d_counts, n, ladder, overlap, Y, X, d_edges, edge_cap,
-                              d_counts + 1, d_state, keep, st, z_sorted);
+    rc = prune_within_enqueue(d_sorted, d_counts, n, ladder, overlap, Y, X, d_edges,
+                              (int)edge_cap, d_counts + 1, d_state, d_keep, st, grid, d_cells,
+                              nullptr);
     if (rc) return rc;
     MMB_CHECK_CUDA(cudaMemcpyAsync(&n_edges, d_counts + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
     MMB_CHECK_CUDA(cudaStreamSynchronize(st));
@@ -295,11 +408,17 @@ int prune_within_impl(const mmb_cand* cand, int n, const double* sigmas_host, in
     if (n_edges <= edge_cap) break;
     edge_cap = n_edges;
   }
+  gather_keep_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(d_keep, d_where, n, keep);
+  MMB_CHECK_LAUNCH();
   MMB_CHECK_CUDA(cudaFreeAsync(d_state, st));
+  MMB_CHECK_CUDA(cudaFreeAsync(d_sorted, st));
+  MMB_CHECK_CUDA(cudaFreeAsync(d_where, st));
+  MMB_CHECK_CUDA(cudaFreeAsync(d_keep, st));
+  MMB_CHECK_CUDA(cudaFreeAsync(d_cells, st));
   MMB_CHECK_CUDA(cudaFreeAsync(d_counts, st));
   MMB_CHECK_CUDA(cudaStreamSynchronize(st));
   if (n_edges > edge_cap) {
-    set_error("kill-edge buffer overflow (%d > %d)", n_edges, edge_cap);
+    set_error("kill-edge buffer overflow (%d > %lld)", n_edges, (long long)edge_cap);
     return MMB_ERR_OVERFLOW;
   }
   return MMB_OK;

@@ -1,20 +1,21 @@
 """Device-resident blob tables: the per-chunk survivors stay in HBM, are merged
-and seam-pruned there, and reach the host once as the final table.
+and seam-pruned there by the library's table kernels, and reach the host once as
+the final table.
 
 Same results, row for row, as the host-side route through
 ``StackDetector.detect_blobs_sub_rois`` -> ``chunking.merge_blobs`` ->
 ``StackPruner.prune_blobs_mp`` (``magmap/cv/stack_detect.py:175-257, 680-861``,
-``chunking.py:410-445``); ``tests/test_gpu_api.py`` compares the two.  What moves
-to the device is index bookkeeping (sorting rows into ``peak_local_max`` order,
-selecting the blobs of a seam slab, concatenating survivors) done with torch
-tensor ops, plus the box match of ``remove_close_blobs`` which is the library's
-``mmb_prune_seams`` kernel.  The host route copies a (N, 14) float64 table several
-times per seam; at config-2 scale (2.6e5 blobs) that is 50-80 ms of a 430 ms
-step and, with several GPUs, serial work on rank 0.
+``chunking.py:410-445``); ``tests/test_gpu_api.py`` compares the two.  A blob
+travels as a 32-byte ``mmb_row`` (``include/mmb200.h``); merge ordering, seam
+classification, the box match of ``remove_close_blobs``, the coordinate
+averaging and the final column layout are ``mmb_stack_tables``
+(``csrc/tables.cu``: hand-written radix sort, counting-sort buckets, match and
+gather kernels - no library sort or select, no host synchronisation).  torch only
+holds the buffers.
 """
 from __future__ import annotations
 
-import math
+import ctypes as C
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -22,174 +23,159 @@ import pandas as pd
 import torch
 
 from . import detector
+from .. import _lib
 
 N_COLS = 11          # Blobs.Cols
-N_MERGED = 14        # + chunk coordinate (chunking.merge_blobs)
-
-
-class ChunkTables:
-    """Survivors of every chunk, kept on the device in arrival order."""
-
-    def __init__(self, device):
-        self.device = device
-        self.parts: List[torch.Tensor] = []      # (n, 5) int32 candidate records
-        self.meta: List[tuple] = []              # (n, coord, offset, (Y, X), sigmas, channel)
-
-    def append(self, cand: torch.Tensor, coord, offset, shape_yx, sigmas, channel: int,
-               grid_rank: Optional[int] = None) -> None:
-        """``grid_rank`` = position of the chunk in the C-ordered chunk grid; chunks
-        may arrive in any order (strip-wise streaming walks y first), the merged
-        table is always in grid order.  Default: arrival order."""
-        if cand.shape[0] == 0:
-            return
-        self.parts.append(cand)
-        self.meta.append((int(cand.shape[0]), tuple(int(c) for c in coord),
-                          tuple(float(o) for o in offset), (int(shape_yx[0]), int(shape_yx[1])),
-                          np.asarray(sigmas, dtype=np.float64), int(channel),
-                          len(self.meta) if grid_rank is None else int(grid_rank)))
-
-    def merged(self) -> Optional[torch.Tensor]:
-        """(N, 14) float64 device table in the layout and row order of
-        ``chunking.merge_blobs`` over ``Blobs.format_blobs`` tables: chunks in
-        grid order, channels in request order inside a chunk, rows of one
-        detection in ``peak_local_max`` order (descending response, ties in C
-        order of (z, y, x, scale))."""
-        if not self.parts:
-            return None
-        dev = self.device
-        cand = torch.cat(self.parts)
-        counts = torch.tensor([m[0] for m in self.meta], device=dev)
-        T = len(self.meta)
-        tix = torch.repeat_interleave(torch.arange(T, device=dev), counts)
-        n_sig = max(len(m[4]) for m in self.meta)
-        sig = np.zeros((T, n_sig))
-        for i, m in enumerate(self.meta):
-            sig[i, :len(m[4])] = m[4]
-        # sort key of a detection: chunk position in the grid, then arrival (channels of
-        # one chunk arrive in request order)
-        seq = sorted(range(T), key=lambda i: (self.meta[i][6], i))
-        place = [0] * T
-        for pos, i in enumerate(seq):
-            place[i] = pos
-        per = torch.tensor(
-            [list(m[1]) + list(m[2]) + [m[3][0], m[3][1], len(m[4]), m[5], place[i]]
-             for i, m in enumerate(self.meta)],
-            dtype=torch.float64, device=dev)                     # (T, 11)
-        sig_t = torch.from_numpy(sig).to(dev)
-        row = per[tix]
-        z, y, x, s = (cand[:, k].long() for k in range(4))
-        resp = cand[:, 4].contiguous().view(torch.float32)
-        Y, X, S = row[:, 6].long(), row[:, 7].long(), row[:, 8].long()
-        lin = ((z * Y + y) * X + x) * S + s
-        # three stable sorts, least significant key first
-        o = torch.sort(lin, stable=True).indices
-        o = o[torch.sort(resp[o], descending=True, stable=True).indices]
-        o = o[torch.sort(row[:, 10].long()[o], stable=True).indices]
-        out = torch.empty((cand.shape[0], N_MERGED), dtype=torch.float64, device=dev)
-        zyx = torch.stack((z, y, x), dim=1).double() + row[:, 3:6]
-        out[:, 0:3] = zyx
-        out[:, 3] = sig_t[tix, s] * math.sqrt(3)
-        out[:, 4] = -1.0
-        out[:, 5] = -1.0
-        out[:, 6] = row[:, 9]
-        out[:, 7:10] = zyx
-        out[:, 10] = -1.0
-        out[:, 11:14] = row[:, 0:3]
-        return out[o]
-
+ROW_INTS = 8         # mmb_row as int32 words
+_MAX_SEC = 128       # seam_counts pitch of mmb_stack_tables
 
 #: columns of the table ``detect_blobs_blocks`` returns (stack_detect.py:458-467):
 #: relative coordinates replaced by the seam-averaged absolute ones, abs columns dropped
 FINAL_COLS = ["z", "y", "x", "radius", "confirmed", "truth", "channel", "region"]
 
 
-def prune_merged(merged: torch.Tensor, overlap, tol, sub_roi_slices, sub_rois_offsets,
-                 channels: Sequence[int], overlap_padding=None, final_layout: bool = False):
-    """``StackPruner.prune_blobs_mp`` on a device-resident merged table.
+class ChunkTables:
+    """Survivors of every chunk as ``mmb_row`` records, kept on the device in
+    arrival order (the table kernels restore the chunk-grid order)."""
 
-    Returns ``((N', 11) float64 numpy table, DataFrame of pruning ratios)``; the
-    only device-to-host transfer of blob rows is the final table.  With
-    ``final_layout`` the table is already what ``detect_blobs_blocks`` makes of it
-    afterwards (``Blobs.replace_rel_with_abs_blob_coords`` then
-    ``remove_abs_blob_coords(True)``): ``(N', 8)`` in ``FINAL_COLS`` order, built on
-    the device so that the host never copies the wide table."""
-    from .. import gpu
-    if merged is None or merged.shape[0] == 0:
+    def __init__(self, device, channels: Sequence[int]):
+        self.device = device
+        self.channels = [int(c) for c in channels]
+        self.parts: List[torch.Tensor] = []          # (n, 8) int32 = mmb_row records
+        self.sigmas = {}                             # channel -> ladder
+
+    def append(self, cand: torch.Tensor, chunk: int, sigmas, channel: int) -> None:
+        """``cand``: ``(n, 5)`` int32 candidate records of one detection (the
+        survivors of ``mmb_detect_chunk_enqueue``); ``chunk``: position of the chunk
+        in the C-ordered chunk grid.  Converted on the current stream."""
+        self.sigmas.setdefault(int(channel), np.asarray(sigmas, dtype=np.float64))
+        n = int(cand.shape[0])
+        if n == 0:
+            return
+        rows = torch.empty((n, ROW_INTS), dtype=torch.int32, device=self.device)
+        _lib.check(_lib.load().mmb_rows_from_cands(
+            C.c_void_p(cand.data_ptr()), n, int(chunk), self.channels.index(int(channel)),
+            C.c_void_p(rows.data_ptr()),
+            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        self.parts.append(rows)
+
+    def rows(self) -> torch.Tensor:
+        if not self.parts:
+            return torch.zeros((0, ROW_INTS), dtype=torch.int32, device=self.device)
+        return self.parts[0] if len(self.parts) == 1 else torch.cat(self.parts)
+
+    def ladders(self, num_sigma: Optional[int] = None) -> np.ndarray:
+        """``(n_channels, num_sigma)`` ladders in channel-list order (zeros where a
+        channel found nothing and never reported its ladder)."""
+        n_sig = num_sigma or max([len(v) for v in self.sigmas.values()] + [1])
+        out = np.zeros((len(self.channels), n_sig))
+        for i, c in enumerate(self.channels):
+            if c in self.sigmas:
+                out[i, :len(self.sigmas[c])] = self.sigmas[c]
+        return out
+
+
+_pinned: List[Optional[torch.Tensor]] = [None]
+
+
+def _to_host(t: torch.Tensor) -> np.ndarray:
+    """Device table -> fresh numpy array through a cached pinned staging buffer (a
+    pageable copy of a config-2 table costs more than pruning it)."""
+    n = t.numel()
+    if n == 0:
+        return np.zeros(tuple(t.shape), dtype=np.float64)
+    buf = _pinned[0]
+    if buf is None or buf.numel() < n:
+        buf = _pinned[0] = torch.empty(max(n, 1 << 20), dtype=t.dtype).pin_memory()
+    stage = buf[:n].view(t.shape)
+    stage.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return stage.numpy().copy()
+
+
+def _axis_sections(sub_roi_slices, axis: int):
+    n = sub_roi_slices.shape[axis]
+    start = np.zeros(n, dtype=np.int32)
+    size = np.zeros(n, dtype=np.int32)
+    for j in range(n):
+        coord = [0, 0, 0]
+        coord[axis] = j
+        sl = sub_roi_slices[tuple(coord)][axis]
+        start[j], size[j] = sl.start, sl.stop - sl.start
+    return start, size
+
+
+def prune_rows(rows: torch.Tensor, ladders: np.ndarray, overlap, tol, sub_roi_slices,
+               channels: Sequence[int], overlap_padding=None, final_layout: bool = False):
+    """``chunking.merge_blobs`` + ``StackPruner.prune_blobs_mp`` (+ the final column
+    layout of ``detect_blobs_blocks`` with ``final_layout``) on device-resident rows.
+
+    Returns ``(float64 numpy table, DataFrame of pruning ratios)``: ``(N', 8)`` in
+    ``FINAL_COLS`` order with ``final_layout`` (what ``Blobs.replace_rel_with_abs_
+    blob_coords`` + ``remove_abs_blob_coords(True)`` leave), else the ``(N', 11)``
+    ``Blobs.Cols`` table.  The only device-to-host transfer of blob rows is that
+    table; ``(None, None)`` when there are no rows."""
+    n = int(rows.shape[0])
+    if n == 0:
         return None, None
+    lib = _lib.load()
     if overlap_padding is None:
         overlap_padding = tol
+    dev = rows.device
+    rows = rows.contiguous()
+    geom = _lib.MmbStackGeom()
+    keep = []
+    for a in range(3):
+        start, size = _axis_sections(sub_roi_slices, a)
+        keep += [start, size]
+        geom.grid[a] = int(sub_roi_slices.shape[a])
+        geom.overlap[a] = int(np.broadcast_to(overlap, (3,))[a])
+        geom.tol[a] = int(np.broadcast_to(tol, (3,))[a])
+        geom.pad[a] = int(np.broadcast_to(overlap_padding, (3,))[a])
+        geom.start[a] = start.ctypes.data_as(C.POINTER(C.c_int32))
+        geom.size[a] = size.ctypes.data_as(C.POINTER(C.c_int32))
+    lad = np.ascontiguousarray(ladders, dtype=np.float64)
+    ids = np.ascontiguousarray([int(c) for c in channels], dtype=np.int32)
+    geom.n_channels = len(ids)
+    geom.num_sigma = int(lad.shape[1])
+    geom.sigmas = lad.ctypes.data_as(C.POINTER(C.c_double))
+    geom.channel_ids = ids.ctypes.data_as(C.POINTER(C.c_int32))
+    ncols = len(FINAL_COLS) if final_layout else N_COLS
+    out = torch.empty((n, ncols), dtype=torch.float64, device=dev)
+    n_out = torch.zeros(1, dtype=torch.int32, device=dev)
+    counts = torch.zeros((len(ids), 3, _MAX_SEC, 4), dtype=torch.int32, device=dev)
+    work = torch.empty(lib.mmb_stack_tables_work_bytes(n), dtype=torch.uint8, device=dev)
+    _lib.check(lib.mmb_stack_tables(
+        C.c_void_p(rows.data_ptr()), n, C.byref(geom), 1 if final_layout else 0,
+        C.c_void_p(out.data_ptr()), C.c_void_p(n_out.data_ptr()), C.c_void_p(counts.data_ptr()),
+        C.c_void_p(work.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    n_final = int(n_out.item())                       # the one synchronisation
+    table = _to_host(out[:n_final])
+    cnt = counts.cpu().numpy()
     cols = ("blobs", "ratio_pruning", "ratio_adjacent")
     ratios_out = {}
-    rel = merged[:, 0:3].contiguous()
-    rel_i = rel.to(torch.int32)          # the reference matches on integer-cast coordinates
-    abs_zyx = merged[:, 7:10].contiguous()
-    tags = merged[:, 11:14].long()
-    chl_col = merged[:, 6]
-    tol_i = [int(t) for t in np.broadcast_to(tol, (3,))]
-    last = tuple(np.subtract(sub_roi_slices.shape, 1))
-    order = []
-    for chl in channels:
-        cur = torch.nonzero(chl_col == float(chl)).flatten()
+    for ci in range(len(ids)):
         for axis in range(3):
-            n_sec = sub_rois_offsets.shape[axis]
-            if n_sec <= 1:
-                continue
-            pos = rel[cur, axis]
-            tag = tags[cur, axis]
-            keep_parts, seam_parts = [], []
-            for j in range(n_sec):
-                coord = [0, 0, 0]
-                coord[axis] = j
-                coord = tuple(coord)
-                start = float(sub_rois_offsets[coord][axis])
-                sl = sub_roi_slices[coord]
-                size = sl[axis].stop - sl[axis].start
-                end = start + size
-                shift = float(overlap[axis] + overlap_padding[axis])
-                if j < n_sec - 1:
-                    lo, hi = end - shift, end + float(overlap_padding[axis])
-                    in_slab = torch.nonzero((pos >= lo) & (pos < hi)).flatten()
-                    n_next = None
-                    nlo = end + float(tol[axis])
-                    nhi = nlo + float(overlap[axis]) + 2 * float(overlap_padding[axis])
-                    total = float(sub_rois_offsets[last][axis]) + size
-                    if nlo < total and nhi < total:
-                        n_next = int(((pos >= nlo) & (pos < nhi)).sum().item())
-                    t = tag[in_slab]
-                    master = cur[in_slab[t == j]]
-                    check = cur[in_slab[t == j + 1]]
-                    if master.shape[0] and check.shape[0]:
-                        m_last, hit = gpu.prune_seams(rel_i[master].contiguous(),
-                                                      rel_i[check].contiguous(), tol_i)
-                        sel = m_last >= 0
-                        ms = master[sel]
-                        if ms.shape[0]:
-                            abs_zyx[ms] = torch.round(
-                                (abs_zyx[ms] + abs_zyx[check[m_last[sel].long()]]) / 2)
-                        check = check[~hit.bool()]
-                    seam_parts.append(master)
-                    seam_parts.append(check)
-                    if n_next is not None:
-                        ratios = detector.meas_pruning_ratio(
-                            int(in_slab.shape[0]), int(master.shape[0] + check.shape[0]), n_next)
-                        if ratios:
-                            for c, v in zip(cols, ratios):
-                                ratios_out.setdefault(c, []).append(v)
-                    upper = lo
-                else:
-                    upper = end
-                lower = start + (shift if j > 0 else 0.0)
-                keep_parts.append(cur[torch.nonzero((pos < upper) & (pos >= lower)).flatten()])
-            cur = torch.cat(keep_parts + seam_parts)
-        order.append(cur)
-    order = order[0] if len(order) == 1 else torch.cat(order)
-    if final_layout:
-        out = torch.empty((order.shape[0], len(FINAL_COLS)), dtype=torch.float64,
-                          device=merged.device)
-        out[:, 0:3] = abs_zyx[order]
-        out[:, 3:7] = merged[order, 3:7]
-        out[:, 7] = merged[order, 10]
-        return out.cpu().numpy(), pd.DataFrame(ratios_out)
-    out = merged[order, :N_COLS]
-    out[:, 7:10] = abs_zyx[order]
-    return out.cpu().numpy(), pd.DataFrame(ratios_out)
+            for j in range(int(sub_roi_slices.shape[axis]) - 1):
+                in_slab, after, n_next, _ = (int(v) for v in cnt[ci, axis, j])
+                r = detector.meas_pruning_ratio(in_slab, after, n_next)
+                if r:
+                    for c, v in zip(cols, r):
+                        ratios_out.setdefault(c, []).append(v)
+    return table, pd.DataFrame(ratios_out)
+
+
+def cands_to_table(cand: torch.Tensor, sigmas, shape_zyx: Sequence[int], channel: int
+                   ) -> Optional[np.ndarray]:
+    """The ``(n, 11)`` table of ``detector.detect_blobs`` for the survivors of ONE
+    detection over a volume of ``shape_zyx`` (``peak_local_max`` order: descending
+    response, ties in C order), built by the table kernels."""
+    if int(cand.shape[0]) == 0:
+        return None
+    tables = ChunkTables(cand.device, [channel])
+    tables.append(cand, 0, sigmas, channel)
+    slices = np.empty((1, 1, 1), dtype=object)
+    slices[0, 0, 0] = tuple(slice(0, int(s)) for s in shape_zyx[:3])
+    table, _ = prune_rows(tables.rows(), tables.ladders(), (0, 0, 0), (0, 0, 0), slices,
+                          [channel])
+    return table

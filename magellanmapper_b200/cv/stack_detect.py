@@ -91,6 +91,23 @@ def setup_blocks(settings, shape: Sequence[int]) -> Blocks:
                   overlap, overlap_padding, max_pixels)
 
 
+def channel_ladders(img, denoise_max_shape, channels: Sequence[int]) -> np.ndarray:
+    """``(n_channels, num_sigma)`` sigma ladders of a pass over ``img`` (numpy array or
+    tensor; only its dtype matters): what ``StackDetector.enqueue_sub_roi`` hands to the
+    library for every chunk, without needing a chunk to have run (ranks of a multi-GPU
+    job that own no chunk still format the gathered table)."""
+    import torch
+    scale = detector.calc_scaling_factor()[2]
+    is_f32 = (img.dtype == np.float32) if isinstance(img, np.ndarray) else (
+        img.dtype == torch.float32)
+    lads = [detector.sigma_ladder(config.get_roi_profile(c), scale,
+                                  is_f32 and denoise_max_shape is None) for c in channels]
+    out = np.zeros((len(lads), max(len(v) for v in lads)))
+    for i, v in enumerate(lads):
+        out[i, :len(v)] = v
+    return out
+
+
 class StackDetector(object):
     """Detects blobs sub-ROI by sub-ROI.  Class attributes carry the shared
     state like the reference's fork-friendly design; here they also cache the
@@ -204,16 +221,15 @@ class StackDetector(object):
                                      denoise_max_shape, channel, coords=None,
                                      prefix=None, suffix=None, tables=None):
         """``detect_blobs_sub_rois`` with the per-chunk tables left on the device:
-        returns the merged (N, 14) float64 CUDA tensor of
-        ``device_tables.ChunkTables.merged`` (None when nothing was found) instead
-        of an object array of host tables.  No ``exclude_border`` support (the
-        caller falls back to the host route for that).  ``prefix`` / ``suffix``
-        (device tensors of whole planes around a HOST ``img``, see
-        ``gpu.StripFeeder``) let ``multi_gpu`` stream a rank's own planes from host
+        returns a ``device_tables.ChunkTables`` (the survivors of every chunk as
+        ``mmb_row`` records in HBM) instead of an object array of host tables;
+        ``device_tables.prune_rows`` turns it into the final table.  No
+        ``exclude_border`` support (the caller takes the host route for that).
+        ``prefix`` / ``suffix`` (device tensors of whole planes around a HOST ``img``,
+        see ``gpu.StripFeeder``) let ``multi_gpu`` stream a rank's own planes from host
         memory while the halo planes of its neighbours are already in HBM.  With
-        ``tables`` (a ``device_tables.ChunkTables``) the survivors are appended to it
-        and it is returned unmerged, so several calls on different pieces of a
-        volume can feed one table."""
+        ``tables`` the survivors are appended to an existing ``ChunkTables``, so
+        several calls on different pieces of a volume can feed one table."""
         from collections import deque
         from .. import gpu
         from . import device_tables
@@ -252,9 +268,9 @@ class StackDetector(object):
         if n_chl > det.n_slots - 1:
             cls._gpu_detector = None
             cls._gpu_detector = det = gpu.ChunkDetector(det.max_shape, n_slots=2 * n_chl)
-        merge = tables is None
         if tables is None:
-            tables = device_tables.ChunkTables(det.device)
+            tables = device_tables.ChunkTables(
+                det.device, plot_3d.setup_channels(img, channel, 3)[1])
         pending = deque()
 
         # The trailing chunks of a grid are thin (12 planes, or 48 voxels wide in
@@ -294,7 +310,9 @@ class StackDetector(object):
             rank_in_grid = int(np.ravel_multi_index(coord, grid))
             for chl, sigmas, ticket in tickets:
                 cand, _ = det_.collect_device(ticket)
-                tables.append(cand, coord, offset, shape[1:3], sigmas, chl, rank_in_grid)
+                # the survivors were copied on the stream the chunk ran on: tag them there
+                with torch.cuda.stream(ticket.stream or main):
+                    tables.append(cand, rank_in_grid, sigmas, chl)
             if strip is not None:
                 in_flight[strip] -= 1
                 if in_flight[strip] == 0 and strip in closed:
@@ -354,7 +372,7 @@ class StackDetector(object):
             finish_oldest()
         if side is not None:
             main.wait_stream(side)           # the side stream's table copies
-        return tables.merged() if merge else tables
+        return tables
 
     @classmethod
     def detect_blobs_sub_rois(cls, img5d, img, sub_roi_slices, sub_rois_offsets,
@@ -577,14 +595,14 @@ def detect_blobs_blocks(filename_base: str, img5d: np_io.Image5d,
     if blocks.exclude_border is None and DEVICE_TABLES and not coloc:
         # per-chunk tables stay in HBM; merged, seam-pruned there, one copy back
         from . import device_tables
-        merged = StackDetector.detect_blobs_sub_rois_device(
+        tables = StackDetector.detect_blobs_sub_rois_device(
             roi, blocks.sub_roi_slices, blocks.sub_rois_offsets, blocks.denoise_max_shape,
             channels)
         detection_time = time() - t_det
         t_prune = time()
-        segments_all, df_pruning = device_tables.prune_merged(
-            merged, blocks.overlap, blocks.tol, blocks.sub_roi_slices,
-            blocks.sub_rois_offsets, channels, blocks.overlap_padding, final_layout=True)
+        segments_all, df_pruning = device_tables.prune_rows(
+            tables.rows(), tables.ladders(), blocks.overlap, blocks.tol, blocks.sub_roi_slices,
+            channels, blocks.overlap_padding, final_layout=True)
         final_on_device = True
         pruning_time = time() - t_prune
     else:

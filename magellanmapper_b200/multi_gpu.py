@@ -260,7 +260,10 @@ def gather_rows(rows: Optional[np.ndarray], n_cols: int, group=None, dst: int = 
 def gather_tensor_rows(rows: Optional[torch.Tensor], n_cols: int, group=None, dst: int = 0,
                        dtype=torch.float64, device=None) -> Optional[List[torch.Tensor]]:
     """``gather_rows`` for tables that already live on the communication device
-    (CUDA tensors under NCCL): no host staging on either side."""
+    (CUDA tensors under NCCL): no host staging on either side.  Row counts travel by
+    ``all_gather``; the payloads are ONE batch of point-to-point operations
+    (``batch_isend_irecv``: every receive of ``dst`` is posted at once, so the
+    transfers of all ranks overlap on NVLink instead of queueing rank by rank)."""
     rank, world = _world(group)
     dev = device if device is not None else (rows.device if rows is not None else
                                              _comm_device(group))
@@ -269,23 +272,27 @@ def gather_tensor_rows(rows: Optional[torch.Tensor], n_cols: int, group=None, ds
     if world == 1:
         return [mine]
     count = torch.tensor([mine.shape[0]], dtype=torch.int64, device=dev)
-    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(counts, count, group=group)
-    counts = [int(c.item()) for c in counts]
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, count, group=group)
+    counts = [int(c) for c in counts.cpu()]
     g = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
     if rank == dst:
-        out = []
+        out, ops = [], []
         for r in range(world):
             if r == rank:
                 out.append(mine)
-            else:
-                buf = torch.empty((counts[r], n_cols), dtype=dtype, device=dev)
-                if counts[r]:
-                    dist.recv(buf, src=g(r), group=group)
-                out.append(buf)
+                continue
+            buf = torch.empty((counts[r], n_cols), dtype=dtype, device=dev)
+            out.append(buf)
+            if counts[r]:
+                ops.append(dist.P2POp(dist.irecv, buf, g(r), group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
         return out
     if mine.shape[0]:
-        dist.send(mine, dst=g(dst), group=group)
+        for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, mine, g(dst), group)]):
+            req.wait()
     return None
 
 
@@ -462,7 +469,7 @@ def detect_blobs_blocks_slabs(filename_base: str, slab, held: Sequence[Range],
         from .cv import device_tables
         dev = torch.device("cuda", torch.cuda.current_device()) if host_slab else slab.device
         boxes = _exchange_boxes(slab, held, loans, z_bounds, y_bounds, group, dev)
-        tables = device_tables.ChunkTables(dev)
+        tables = device_tables.ChunkTables(dev, channels)
         if coords:
             stack_detect.StackDetector.detect_blobs_sub_rois_device(
                 ext, local_slices, blocks.sub_rois_offsets, blocks.denoise_max_shape,
@@ -480,19 +487,17 @@ def detect_blobs_blocks_slabs(filename_base: str, slab, held: Sequence[Range],
             stack_detect.StackDetector.detect_blobs_sub_rois_device(
                 box, box_slices, blocks.sub_rois_offsets, blocks.denoise_max_shape, channels,
                 coords=unit, tables=tables)
-        merged = tables.merged()
-        parts = gather_tensor_rows(merged, device_tables.N_MERGED, group, device=dev)
+        # 32-byte rows travel; rank 0 orders them by chunk (whoever worked on it), prunes
+        # the seams and formats the table with the library's table kernels
+        parts = gather_tensor_rows(tables.rows(), device_tables.ROW_INTS, group,
+                                   dtype=torch.int32, device=dev)
         if rank != 0:
             return None, None, None
-        allm = torch.cat(parts)
-        if loans and allm.shape[0]:
-            # lent units arrive with their worker's table: restore chunk-grid order
-            tg = allm[:, 11:14].long()
-            key = (tg[:, 0] * grid[1] + tg[:, 1]) * grid[2] + tg[:, 2]
-            allm = allm[torch.sort(key, stable=True).indices]
-        segments_all, df_pruning = device_tables.prune_merged(
-            allm, blocks.overlap, blocks.tol, blocks.sub_roi_slices,
-            blocks.sub_rois_offsets, channels, blocks.overlap_padding, final_layout=True)
+        allr = parts[0] if len(parts) == 1 else torch.cat(parts)
+        segments_all, df_pruning = device_tables.prune_rows(
+            allr, stack_detect.channel_ladders(slab, blocks.denoise_max_shape, channels),
+            blocks.overlap, blocks.tol, blocks.sub_roi_slices, channels,
+            blocks.overlap_padding, final_layout=True)
         final_on_device = True
     else:
         seg_rois = None
@@ -626,17 +631,26 @@ def _seamless_setup(global_shape, channel):
 
 
 def seamless_candidates(ext, ext_range: Range, own_range: Range, global_shape: Sequence[int],
-                        channel: int = 0, tile_yx: Optional[Sequence[int]] = None) -> np.ndarray:
+                        channel: int = 0, tile_yx: Optional[Sequence[int]] = None,
+                        capacity: Optional[int] = None) -> torch.Tensor:
     """The local part of ``detect_seamless``: local maxima (no pruning) of the
     planes ``own_range`` given the planes ``ext_range`` (own + halo) of the volume,
-    in GLOBAL coordinates, as ``gpu.CAND_DTYPE`` records."""
-    from . import gpu
+    in GLOBAL coordinates, as an ``(n, 5)`` int32 CUDA tensor of ``mmb_cand`` records
+    (arbitrary order).  y and x are tiled with the same halo when ``tile_yx`` is given;
+    every tile's chunk is enqueued asynchronously and its owned candidates are appended
+    to one device list (``mmb_cands_append``), so nothing but three counters per tile
+    crosses to the host."""
+    import ctypes as C
+    from collections import deque
+    from . import gpu, _lib
+    lib = _lib.load()
     settings, pre, sigmas, halo, bd = _seamless_setup(global_shape, channel)
     Z, Y, X = (int(v) for v in global_shape[:3])
     e0, e1 = ext_range
     z0, z1 = own_range
+    dev = ext.device
     if z1 <= z0:
-        return np.zeros(0, dtype=gpu.CAND_DTYPE)
+        return torch.zeros((0, 5), dtype=torch.int32, device=dev)
     if e0 % bd[0] != 0 or (e1 % bd[0] != 0 and e1 != Z):
         raise ValueError(f"extended range {ext_range} is not aligned to the block depth {bd[0]}")
     if (z0 - e0 < halo and e0 > 0) or (e1 - z1 < halo and e1 < Z):
@@ -651,26 +665,42 @@ def seamless_candidates(ext, ext_range: Range, own_range: Range, global_shape: S
     hy = -(-halo // bd[1]) * bd[1]
     hx = -(-halo // bd[2]) * bd[2]
     det = gpu.ChunkDetector((e1 - e0, min(Y, ty + 2 * hy), min(X, tx + 2 * hx)))
-    cands = []
-    for y0 in range(0, Y, ty):
-        for x0 in range(0, X, tx):
-            ya, yb = max(0, y0 - hy), min(Y, y0 + ty + hy)
-            xa, xb = max(0, x0 - hx), min(X, x0 + tx + hx)
-            view = ext[:, ya:yb, xa:xb]
-            src = gpu.as_source(view, channel if ext.dim() == 4 else None)
-            # overlap 1.0 = no pruning here: _prune_blobs runs once over all slabs
-            got, _ = det.detect(src, sigmas, settings["detection_threshold"], 1.0,
-                                scale=in_scale, pre=pre, block_shape=bd,
-                                z_lo=z0 - e0, z_hi=z1 - e0)
-            if len(got):
-                yy, xx = got["y"] + ya, got["x"] + xa
-                keep = (yy >= y0) & (yy < min(Y, y0 + ty)) & (xx >= x0) & (xx < min(X, x0 + tx))
-                got = got[keep].copy()
-                got["z"] += e0
-                got["y"] += ya
-                got["x"] += xa
-                cands.append(got)
-    return np.concatenate(cands) if cands else np.zeros(0, dtype=gpu.CAND_DTYPE)
+    own_vox = (z1 - z0) * Y * X
+    cap = int(capacity) if capacity else max(1 << 16, own_vox // 512)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    while True:
+        out = torch.empty((cap, 5), dtype=torch.int32, device=dev)
+        counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        pending = deque()
+
+        def finish_oldest():
+            ticket, (ya, xa, y0, x0) = pending.popleft()
+            got, _ = det.collect_device(ticket)
+            n = int(got.shape[0])
+            if n:
+                _lib.check(lib.mmb_cands_append(
+                    C.c_void_p(got.data_ptr()), n, None, _lib._I32x3(e0, ya, xa),
+                    _lib._I32x3(z0, y0, x0),
+                    _lib._I32x3(z1, min(Y, y0 + ty), min(X, x0 + tx)),
+                    C.c_void_p(out.data_ptr()), cap, C.c_void_p(counter.data_ptr()), stream))
+
+        for y0 in range(0, Y, ty):
+            for x0 in range(0, X, tx):
+                ya, yb = max(0, y0 - hy), min(Y, y0 + ty + hy)
+                xa, xb = max(0, x0 - hx), min(X, x0 + tx + hx)
+                src = gpu.as_source(ext[:, ya:yb, xa:xb], channel if ext.dim() == 4 else None)
+                while pending and det.free_slots() < 1:
+                    finish_oldest()
+                # overlap 1.0 = no pruning here: _prune_blobs runs once over all slabs
+                pending.append((det.enqueue(src, sigmas, settings["detection_threshold"], 1.0,
+                                            scale=in_scale, pre=pre, block_shape=bd,
+                                            z_lo=z0 - e0, z_hi=z1 - e0), (ya, xa, y0, x0)))
+        while pending:
+            finish_oldest()
+        n = int(counter.item())
+        if n <= cap:
+            return out[:n]
+        cap = int(n * 1.1) + 1024          # the list overflowed: redo with room for all
 
 
 def detect_seamless(slab, held: Sequence[Range], global_shape: Sequence[int],
@@ -680,14 +710,14 @@ def detect_seamless(slab, held: Sequence[Range], global_shape: Sequence[int],
     Each rank: exchange halo planes, run the fused chunk driver on its extended
     slab without pruning and keep the local maxima of the planes it owns
     (``z_lo``/``z_hi`` of ``mmb_detect_chunk_enqueue``); rank 0: gather the
-    candidates and run ``_prune_blobs`` once over all of them
-    (``mmb_prune_within_zsorted``).  ``tile_yx`` additionally tiles y and x inside
+    candidates (device to device, one batch of NCCL send/recv) and run
+    ``_prune_blobs`` once over all of them (``mmb_prune_within``: cell-bucketed
+    pair search, any listing order).  ``tile_yx`` additionally tiles y and x inside
     a rank (tile + halo must fit the workspace of eight float volumes).
 
     Returns on rank 0 the ``(n, 11)`` blob table of ``detector.detect_blobs`` in
     ``peak_local_max`` order (None if empty), None elsewhere.
     """
-    from . import gpu
     rank, world = _world(group)
     settings, pre, sigmas, halo, bd = _seamless_setup(global_shape, channel)
     Z, Y, X = (int(v) for v in global_shape[:3])
@@ -695,27 +725,33 @@ def detect_seamless(slab, held: Sequence[Range], global_shape: Sequence[int],
     # the caller's slabs need not coincide with the block-aligned owned slabs
     ext = exchange_planes(slab, held, ext_ranges, group)
     mine = seamless_candidates(ext, ext_ranges[rank], own[rank], (Z, Y, X), channel, tile_yx)
-    raw = np.ascontiguousarray(mine).view(np.int32).reshape(-1, 5)
-    parts = gather_rows(raw, 5, group, dtype=np.int32)
+    del ext
+    parts = gather_tensor_rows(mine, 5, group, dtype=torch.int32, device=mine.device)
     if rank != 0:
         return None
-    allc = np.ascontiguousarray(np.concatenate(parts).astype(np.int32)).reshape(-1).view(
-        gpu.CAND_DTYPE)
+    allc = parts[0] if len(parts) == 1 else torch.cat(parts)
     return prune_global(allc, sigmas, settings["overlap"], (Z, Y, X), channel)
 
 
-def prune_global(cands: np.ndarray, sigmas, overlap: float, shape: Sequence[int], channel: int):
-    """``_prune_blobs`` over the candidates of the whole volume, then the blob
-    table of ``detector.detect_blobs`` in ``peak_local_max`` order."""
-    from . import gpu
-    from .cv import detector
-    if len(cands) == 0:
+def prune_global(cands, sigmas, overlap: float, shape: Sequence[int], channel: int):
+    """``_prune_blobs`` over the candidates of the whole volume (``(n, 5)`` int32 CUDA
+    tensor, or ``gpu.CAND_DTYPE`` records on the host), then the blob table of
+    ``detector.detect_blobs`` in ``peak_local_max`` order - all on the device."""
+    import ctypes as C
+    from . import gpu, _lib
+    from .cv import device_tables
+    if isinstance(cands, np.ndarray):
+        cands = gpu.cands_from_numpy(cands)
+    n = int(cands.shape[0])
+    if n == 0:
         return None
     Z, Y, X = (int(v) for v in shape)
-    # z-sorted input lets the pair kernel skip tiles farther than the cut-off
-    order = np.argsort(cands["z"], kind="stable")
-    cands = cands[order]
-    dev = gpu.cands_from_numpy(cands)
-    keep = gpu.prune_within(dev, len(cands), sigmas, overlap, Y, X, z_sorted=True)
-    keep = keep.cpu().numpy().astype(bool)
-    return detector.cands_to_blobs(cands[keep], sigmas, (Y, X), channel)
+    cands = cands.contiguous()
+    keep = gpu.prune_within(cands, n, sigmas, overlap, Y, X)
+    kept = torch.empty_like(cands)
+    counter = torch.zeros(1, dtype=torch.int32, device=cands.device)
+    _lib.check(_lib.load().mmb_cands_append(
+        C.c_void_p(cands.data_ptr()), n, C.c_void_p(keep.data_ptr()), _lib._I32x3(0, 0, 0),
+        _lib._I32x3(0, 0, 0), _lib._I32x3(Z, Y, X), C.c_void_p(kept.data_ptr()), n,
+        C.c_void_p(counter.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return device_tables.cands_to_table(kept[:int(counter.item())], sigmas, (Z, Y, X), channel)

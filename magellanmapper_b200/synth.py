@@ -63,3 +63,26 @@ def near_max_of(vol: np.ndarray, pct: float = 99.5) -> float:
     """The reference's ``near_max`` metadata: the max over z-planes of the
     per-plane upper percentile (``magmap/io/importer.py:1415-1468``)."""
     return float(max(np.percentile(p, pct) for p in vol))
+
+
+def device_volume(shape: Sequence[int], seed: int, offset: Sequence[int] = (0, 0, 0),
+                  density: float = DENSITY, device=None, out=None):
+    """The same recipe generated ON THE DEVICE as a pure function of (seed, global
+    z, y, x) (``mmb_synth_nuclei``, include/mmb200_tools.h): returns the uint16 box of
+    ``shape`` whose first voxel sits at ``offset`` of the unbounded volume, as an
+    int16-bit CUDA tensor (torch has no full uint16).  Boxes generated separately -
+    the z-slabs of the ranks, a halo, the sub-box an oracle spot check recomputes -
+    agree bit for bit where they overlap.  Not the numpy generator's values: a
+    different random stream of the same distribution."""
+    import ctypes as C
+    import torch
+    from . import _lib, gpu
+    dev = device or gpu.require_cuda()
+    Z, Y, X = (int(v) for v in shape[:3])
+    if out is None:
+        out = torch.empty((Z, Y, X), dtype=torch.int16, device=dev)
+    _lib.check(_lib.load().mmb_synth_nuclei(
+        C.c_void_p(out.data_ptr()), Z, Y, X, int(offset[0]), int(offset[1]), int(offset[2]),
+        int(seed) & 0xFFFFFFFFFFFFFFFF, float(density),
+        C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return out

@@ -8,8 +8,8 @@ from magellanmapper_b200 import _lib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
-    text = open(os.path.join(ROOT, "include", "mmb200.h")).read()
+def _declared_symbols(header="mmb200.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(mmb_[a-z0-9_]+)\s*\(", text)))
 
@@ -22,6 +22,10 @@ def test_library_loads_and_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in mmb200.h but not exported"
     assert set(declared) == set(_lib.SIGNATURES), "ctypes table out of sync with the header"
     assert lib.mmb_version() == 1
+    tools = _declared_symbols("mmb200_tools.h")
+    assert set(tools) == set(_lib.TOOLS_SIGNATURES)
+    for name in tools:
+        assert hasattr(lib, name), f"{name} declared in mmb200_tools.h but not exported"
 
 
 def test_struct_layouts_match_header():

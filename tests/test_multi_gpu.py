@@ -175,6 +175,15 @@ def _gloo_worker(rank, world, port, out_dir):
         else:
             assert parts is None and cparts is None
         assert mg._agree_max(7 + rank) == 8
+        # device-table gather: one batch of point-to-point transfers, int32 mmb_row records
+        rows = (torch.arange(8 * (2 + rank), dtype=torch.int32) + 1000 * rank).reshape(-1, 8)
+        tparts = mg.gather_tensor_rows(rows if rank == 1 else None, 8, dtype=torch.int32,
+                                       device=torch.device("cpu"))
+        if rank == 0:
+            assert tparts[0].shape == (0, 8) and tparts[1].shape == (3, 8)
+            assert torch.equal(tparts[1], (torch.arange(24, dtype=torch.int32) + 1000).reshape(3, 8))
+        else:
+            assert tparts is None
         open(os.path.join(out_dir, f"ok{rank}"), "w").close()
     finally:
         dist.destroy_process_group()
@@ -275,7 +284,8 @@ def test_seamless_slabs_equal_one_chunk(tile_yx):
     own, ext = mg.seamless_plan(shape[0], 3, bd[0], halo)
     cands = [mg.seamless_candidates(dev[e0:e1], (e0, e1), o, shape, 0, tile_yx)
              for o, (e0, e1) in zip(own, ext)]
-    got = mg.prune_global(np.concatenate(cands), sigmas, settings["overlap"], shape, 0)
+    assert all(c.is_cuda and c.dtype == torch.int32 for c in cands)
+    got = mg.prune_global(torch.cat(cands), sigmas, settings["overlap"], shape, 0)
     assert len(want) > 50
     np.testing.assert_array_equal(got, want)
 
@@ -287,6 +297,8 @@ def _nccl_worker(rank, world, port, out_dir, golden_dir):
     dist.init_process_group("nccl", rank=rank, world_size=world,
                             device_id=torch.device("cuda", rank))
     try:
+        from magellanmapper_b200 import gpu, synth
+        from magellanmapper_b200.cv import detector
         g = np.load(os.path.join(golden_dir, "stack_small.npz"))
         _setup(near_max=float(g["near_max"]), segment_size=50)
         os.chdir(out_dir)
@@ -304,15 +316,52 @@ def _nccl_worker(rank, world, port, out_dir, golden_dir):
             np.testing.assert_array_equal(blobs_h.blobs, g["plain_blobs"])
         else:
             assert blobs is None and blobs_h is None
+        stack_detect.StackDetector.release_workspace()
+        # a taller stack with the default 500-voxel chunks scaled down so that units are
+        # lent between ranks (several chunk rows, y columns and a thin trailing row)
+        shape = (150, 120, 110)
+        big = synth.device_volume(shape, 91, device=torch.device("cuda", rank))
+        nm = float(np.percentile(big.cpu().numpy().view(np.uint16), 99.5))
+        _setup(near_max=nm, segment_size=40)
+        held = mg.slab_bounds(shape[0], world)
+        _, _, b_multi = mg.detect_blobs_blocks_slabs(
+            os.path.join(out_dir, "lend"), big[held[rank][0]:held[rank][1]].contiguous(), held,
+            shape)
+        if rank == 0:
+            from magellanmapper_b200.io import np_io
+            _, _, b_one = stack_detect.detect_blobs_blocks(
+                os.path.join(out_dir, "one"), np_io.Image5d(big[None]), None, None, [0], False,
+                False, True)
+            assert len(b_one.blobs) > 100
+            np.testing.assert_array_equal(b_multi.blobs, b_one.blobs)
+        stack_detect.StackDetector.release_workspace()
+        # seamless z-slabs over NCCL == the whole volume as one chunk on one GPU
+        _setup(near_max=nm)
+        table = mg.detect_seamless(big[held[rank][0]:held[rank][1]].contiguous(), held, shape, 0,
+                                   tile_yx=(50, 75) if world > 2 else None)
+        if rank == 0:
+            settings, pre, sigmas, halo, bd = mg._seamless_setup(shape, 0)
+            det = gpu.ChunkDetector(shape)
+            whole, _ = det.detect(gpu.as_source(big), sigmas, settings["detection_threshold"],
+                                  settings["overlap"], pre=pre, block_shape=bd)
+            want = detector.cands_to_blobs(whole, sigmas, shape[1:], 0)
+            assert len(want) > 50
+            np.testing.assert_array_equal(table, want)
+        else:
+            assert table is None
         open(os.path.join(out_dir, f"ok{rank}"), "w").close()
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.gpu
-def test_slab_driver_nccl_world2(golden_dir, tmp_path):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
+@pytest.mark.parametrize("world", [2, 4])
+def test_slab_drivers_nccl(golden_dir, tmp_path, world):
+    """Both shardings on N real ranks over NCCL (halo exchange, lent units, batched
+    row gather, rank-0 table kernels) against the single-GPU results; runs whenever the
+    box has N GPUs."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     port = _free_port()
-    mp.spawn(_nccl_worker, args=(2, port, str(tmp_path), golden_dir), nprocs=2, join=True)
-    assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
+    mp.spawn(_nccl_worker, args=(world, port, str(tmp_path), golden_dir), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))

@@ -14,15 +14,9 @@ settings = config.get_roi_profile(0)
 blocks = stack_detect.setup_blocks(settings, vol.shape)
 for it in range(3):
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    merged = stack_detect.StackDetector.detect_blobs_sub_rois_device(vol, blocks.sub_roi_slices, blocks.sub_rois_offsets, blocks.denoise_max_shape, [0])
+    tables = stack_detect.StackDetector.detect_blobs_sub_rois_device(vol, blocks.sub_roi_slices, blocks.sub_rois_offsets, blocks.denoise_max_shape, [0])
+    rows = tables.rows()
     torch.cuda.synchronize(); t1 = time.perf_counter()
-    out, df = device_tables.prune_merged(merged, blocks.overlap, blocks.tol, blocks.sub_roi_slices, blocks.sub_rois_offsets, [0], blocks.overlap_padding)
+    out, df = device_tables.prune_rows(rows, tables.ladders(), blocks.overlap, blocks.tol, blocks.sub_roi_slices, [0], blocks.overlap_padding, final_layout=True)
     torch.cuda.synchronize(); t2 = time.perf_counter()
-    print(f"detect {1e3*(t1-t0):.1f} ms  prune {1e3*(t2-t1):.1f} ms  rows {merged.shape[0]} -> {out.shape[0]}")
-# inside merged(): time the table build alone
-import cProfile, pstats
-pr = cProfile.Profile(); pr.enable()
-out, df = device_tables.prune_merged(merged, blocks.overlap, blocks.tol, blocks.sub_roi_slices, blocks.sub_rois_offsets, [0], blocks.overlap_padding)
-torch.cuda.synchronize()
-pr.disable()
-pstats.Stats(pr).sort_stats("tottime").print_stats(12)
+    print(f"detect {1e3*(t1-t0):.1f} ms  prune {1e3*(t2-t1):.1f} ms  rows {rows.shape[0]} -> {out.shape[0]}")
