@@ -98,7 +98,11 @@ int mmb_to_float(const void* in, int dtype, const int64_t in_strides[3],
  * (plot_3d.py:114-172) on every (bz,by,bx) block anchored at the chunk origin:
  * exact np.percentile (linear) -> stretch -> clip -> sigma=8 'nearest' unsharp
  * mask -> octahedron(1) erosion when the stretched block mean > threshold.
- * One CTA per block.  Blocks larger than 32 voxels on any side: UNSUPPORTED.  */
+ * Blocks up to 32 voxels a side: one CTA per block, block resident in shared memory.
+ * Larger blocks - the whole ROI of the GUI path (block shape = volume shape,
+ * magmap/gui/visualizer.py:2742-2743), the `lowres` profile - run as whole-volume
+ * kernels (radix-select percentiles, 65-tap 'nearest' blur per block); any size.
+ * Equal clip_vmin and clip_vmax skip the stretch (denoise_roi on its own).      */
 int mmb_preprocess_blocks(const void* in, int dtype, const int64_t in_strides[3],
                           int Z, int Y, int X, int bz, int by, int bx,
                           const mmb_preproc_params* p, float* out, int64_t pitch,

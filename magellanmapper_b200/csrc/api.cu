@@ -106,7 +106,7 @@ int to_float_impl(const void* in, int dtype, const int64_t st[3], int Z, int Y, 
                   float* out, int64_t pitch, double scale, cudaStream_t s);
 int preprocess_impl(const void* in, int dtype, const int64_t st[3], int Z, int Y, int X, int bz,
                     int by, int bx, const mmb_preproc_params* p, float* out, int64_t pitch,
-                    cudaStream_t s);
+                    cudaStream_t s, void* scratch, int64_t scratch_bytes);
 int log_scale_impl(const float* in, float* out, float* work, int Z, int Y, int X, int64_t pitch,
                    double sigma, cudaStream_t st);
 int localmax_impl(const float* prev, const float* cur, const float* next, int Z, int Y, int X,
@@ -236,7 +236,10 @@ extern "C" int mmb_detect_chunk_enqueue(const void* in, int dtype, const int64_t
   unsigned char* state = (unsigned char*)tail;          tail += L.state_b;
   int* counters = (int*)tail;      // [0] peaks, [1] survivors, [2] edges, [3] order-dependent set
 
-  if (pre) rc = preprocess_impl(in, dtype, in_strides, Z, Y, X, bz, by, bx, pre, F, pitch, st);
+  // blocks above 32 voxels take the global-memory path, which borrows the (still idle)
+  // sweep buffers A..D as scratch
+  if (pre) rc = preprocess_impl(in, dtype, in_strides, Z, Y, X, bz, by, bx, pre, F, pitch, st, lw,
+                                4 * L.vol_b);
   else rc = to_float_impl(in, dtype, in_strides, Z, Y, X, F, pitch, scale, st);
   if (rc) return rc;
 

@@ -24,6 +24,8 @@
 
 namespace mmb {
 
+int64_t preprocess_large_work_bytes(int Z, int Y, int64_t pitch, int bz, int by, int bx);
+
 constexpr int kPreThreads = 640;
 constexpr int kPreMinBlocks = 2;
 
@@ -378,13 +380,20 @@ static int dispatch_nl(const void* in, const PreGeom& g, const mmb_preproc_param
   return launch_pre<T, 32>(in, g, p, mats, mat_pitch, out, st);
 }
 
+int preprocess_large_impl(const void* in, int dtype, const int64_t strides[3], int Z, int Y,
+                          int X, int bz, int by, int bx, const mmb_preproc_params* p, float* out,
+                          int64_t pitch, void* scratch, cudaStream_t st);
+
+// `scratch` / `scratch_bytes`: memory the caller lends to the large-block path (the fused
+// chunk driver's sweep buffers are idle while it preprocesses); may be NULL / 0.
 int preprocess_impl(const void* in, int dtype, const int64_t st[3], int Z, int Y, int X, int bz,
                     int by, int bx, const mmb_preproc_params* p, float* out, int64_t pitch,
-                    cudaStream_t s) {
+                    cudaStream_t s, void* scratch, int64_t scratch_bytes) {
   bz = bz < Z ? bz : Z; by = by < Y ? by : Y; bx = bx < X ? bx : X;
   if (bz > 32 || by > 32 || bx > 32) {
-    set_error("preprocessing block %dx%dx%d exceeds the 32-voxel fast path", bz, by, bx);
-    return MMB_ERR_UNSUPPORTED;
+    // blocks that do not fit one CTA's shared memory: global-memory path
+    if (scratch_bytes < preprocess_large_work_bytes(Z, Y, pitch, bz, by, bx)) scratch = nullptr;
+    return preprocess_large_impl(in, dtype, st, Z, Y, X, bz, by, bx, p, out, pitch, scratch, s);
   }
   PreGeom g;
   g.Z = Z; g.Y = Y; g.X = X; g.bz = bz; g.by = by; g.bx = bx;
@@ -415,5 +424,5 @@ extern "C" int mmb_preprocess_blocks(const void* in, int dtype, const int64_t in
   MMB_REQUIRE(Z > 0 && Y > 0 && X > 0 && pitch >= X, "bad shape");
   MMB_REQUIRE(bz > 0 && by > 0 && bx > 0, "bad block shape");
   return mmb::preprocess_impl(in, dtype, in_strides, Z, Y, X, bz, by, bx, p, out, pitch,
-                              (cudaStream_t)stream);
+                              (cudaStream_t)stream, nullptr, 0);
 }

@@ -463,8 +463,9 @@ class ChunkDetector:
 
 def whole_roi_preprocess(src: Source, params: MmbPreprocParams) -> np.ndarray:
     """``saturate_roi`` / ``denoise_roi`` with the whole ROI as one block (the
-    GUI path).  Only ROIs that fit the one-CTA kernel (<= 32 voxels a side) are
-    implemented so far; larger ones raise ``NotImplementedError``."""
+    GUI path, magmap/gui/visualizer.py:2742-2743).  ROIs up to 32 voxels a side run
+    in the one-CTA kernel, larger ones in the whole-volume kernels of
+    ``preprocess_large.cu`` (any size that fits the device)."""
     Z, Y, X = src.shape
     out = preprocess_blocks(src, (Z, Y, X), params)
     torch.cuda.synchronize()

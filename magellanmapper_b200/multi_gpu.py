@@ -139,24 +139,32 @@ def _comm_device(group=None) -> torch.device:
 
 
 def exchange_planes(local: torch.Tensor, held: Sequence[Range], wanted: Sequence[Range],
-                    group=None) -> torch.Tensor:
+                    group=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Halo exchange.  ``local`` holds planes ``held[rank]`` of the volume
     (dim 0 = z); returns a tensor holding ``wanted[rank]`` (a superset), the
     missing planes received from the ranks that hold them with grouped
-    ``isend/irecv`` (NCCL send/recv over NVLink on the GPUs)."""
+    ``isend/irecv`` (NCCL send/recv over NVLink on the GPUs).  ``out``: a
+    preallocated tensor for ``wanted[rank]``; when ``local`` is already the view of
+    ``out`` that its planes belong to (a slab generated or loaded in place, with room
+    for the halo around it) nothing is copied - at whole-brain size a second copy of
+    the slab would not fit next to the first."""
     rank, world = _world(group)
     h0, h1 = held[rank]
     w0, w1 = wanted[rank]
     if local.shape[0] != h1 - h0:
         raise ValueError(f"rank {rank} holds {local.shape[0]} planes, expected {h1 - h0}")
-    if (w0, w1) == (h0, h1):
+    if out is not None and out.shape[0] != max(0, w1 - w0):
+        raise ValueError(f"out holds {out.shape[0]} planes, expected {w1 - w0}")
+    if (w0, w1) == (h0, h1) and out is None:
         ext = local
     else:
-        ext = torch.empty((max(0, w1 - w0),) + tuple(local.shape[1:]), dtype=local.dtype,
-                          device=local.device)
+        ext = out if out is not None else torch.empty(
+            (max(0, w1 - w0),) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
         a, b = max(w0, h0), min(w1, h1)          # the part of the wanted range held here
         if a < b:
-            ext[a - w0:b - w0].copy_(local[a - h0:b - h0])
+            dst = ext[a - w0:b - w0]
+            if dst.data_ptr() != local[a - h0:b - h0].data_ptr():
+                dst.copy_(local[a - h0:b - h0])
     if world == 1:
         if not (h0 <= w0 and w1 <= h1) and w1 > w0:
             raise ValueError(f"planes {wanted[rank]} are not all held ({held[rank]})")
@@ -636,7 +644,8 @@ def seamless_candidates(ext, ext_range: Range, own_range: Range, global_shape: S
     """The local part of ``detect_seamless``: local maxima (no pruning) of the
     planes ``own_range`` given the planes ``ext_range`` (own + halo) of the volume,
     in GLOBAL coordinates, as an ``(n, 5)`` int32 CUDA tensor of ``mmb_cand`` records
-    (arbitrary order).  y and x are tiled with the same halo when ``tile_yx`` is given;
+    (arbitrary order).  y and x - and z, with a ``(z, y, x)`` triple - are tiled with the
+    same halo when ``tile_yx`` is given;
     every tile's chunk is enqueued asynchronously and its owned candidates are appended
     to one device list (``mmb_cands_append``), so nothing but three counters per tile
     crosses to the host."""
@@ -659,12 +668,23 @@ def seamless_candidates(ext, ext_range: Range, own_range: Range, global_shape: S
     if pre is None:
         probe = gpu.as_source(ext, channel if ext.dim() == 4 else None)
         in_scale = {gpu._lib.MMB_U8: 1 / 255.0, gpu._lib.MMB_U16: 1 / 65535.0}.get(probe.dtype, 1.0)
-    ty, tx = (Y, X) if tile_yx is None else (int(tile_yx[0]), int(tile_yx[1]))
+    # tiles: (y, x) or (z, y, x) voxels of OWNED volume per tile, rounded up to whole
+    # preprocessing blocks; every tile is filtered with a halo of whole block layers
+    tz = z1 - z0
+    if tile_yx is None:
+        ty, tx = Y, X
+    elif len(tile_yx) == 3:
+        tz, ty, tx = (int(v) for v in tile_yx)
+    else:
+        ty, tx = int(tile_yx[0]), int(tile_yx[1])
+    tz = -(-tz // bd[0]) * bd[0]
     ty = -(-ty // bd[1]) * bd[1]
     tx = -(-tx // bd[2]) * bd[2]
+    hz = -(-halo // bd[0]) * bd[0]
     hy = -(-halo // bd[1]) * bd[1]
     hx = -(-halo // bd[2]) * bd[2]
-    det = gpu.ChunkDetector((e1 - e0, min(Y, ty + 2 * hy), min(X, tx + 2 * hx)))
+    det = gpu.ChunkDetector((min(e1 - e0, tz + 2 * hz), min(Y, ty + 2 * hy),
+                             min(X, tx + 2 * hx)))
     own_vox = (z1 - z0) * Y * X
     cap = int(capacity) if capacity else max(1 << 16, own_vox // 512)
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -674,27 +694,32 @@ def seamless_candidates(ext, ext_range: Range, own_range: Range, global_shape: S
         pending = deque()
 
         def finish_oldest():
-            ticket, (ya, xa, y0, x0) = pending.popleft()
+            ticket, (za, ya, xa, t0, t1, y0, x0) = pending.popleft()
             got, _ = det.collect_device(ticket)
             n = int(got.shape[0])
             if n:
                 _lib.check(lib.mmb_cands_append(
-                    C.c_void_p(got.data_ptr()), n, None, _lib._I32x3(e0, ya, xa),
-                    _lib._I32x3(z0, y0, x0),
-                    _lib._I32x3(z1, min(Y, y0 + ty), min(X, x0 + tx)),
+                    C.c_void_p(got.data_ptr()), n, None, _lib._I32x3(za, ya, xa),
+                    _lib._I32x3(t0, y0, x0),
+                    _lib._I32x3(t1, min(Y, y0 + ty), min(X, x0 + tx)),
                     C.c_void_p(out.data_ptr()), cap, C.c_void_p(counter.data_ptr()), stream))
 
-        for y0 in range(0, Y, ty):
-            for x0 in range(0, X, tx):
-                ya, yb = max(0, y0 - hy), min(Y, y0 + ty + hy)
-                xa, xb = max(0, x0 - hx), min(X, x0 + tx + hx)
-                src = gpu.as_source(ext[:, ya:yb, xa:xb], channel if ext.dim() == 4 else None)
-                while pending and det.free_slots() < 1:
-                    finish_oldest()
-                # overlap 1.0 = no pruning here: _prune_blobs runs once over all slabs
-                pending.append((det.enqueue(src, sigmas, settings["detection_threshold"], 1.0,
-                                            scale=in_scale, pre=pre, block_shape=bd,
-                                            z_lo=z0 - e0, z_hi=z1 - e0), (ya, xa, y0, x0)))
+        for t0 in range(z0, z1, tz):
+            t1 = min(z1, t0 + tz)
+            za, zb = max(e0, t0 - hz), min(e1, t1 + hz)
+            for y0 in range(0, Y, ty):
+                for x0 in range(0, X, tx):
+                    ya, yb = max(0, y0 - hy), min(Y, y0 + ty + hy)
+                    xa, xb = max(0, x0 - hx), min(X, x0 + tx + hx)
+                    src = gpu.as_source(ext[za - e0:zb - e0, ya:yb, xa:xb],
+                                        channel if ext.dim() == 4 else None)
+                    while pending and det.free_slots() < 1:
+                        finish_oldest()
+                    # overlap 1.0 = no pruning here: _prune_blobs runs once over all slabs
+                    pending.append((det.enqueue(src, sigmas, settings["detection_threshold"],
+                                                1.0, scale=in_scale, pre=pre, block_shape=bd,
+                                                z_lo=t0 - za, z_hi=t1 - za),
+                                    (za, ya, xa, t0, t1, y0, x0)))
         while pending:
             finish_oldest()
         n = int(counter.item())
@@ -704,7 +729,8 @@ def seamless_candidates(ext, ext_range: Range, own_range: Range, global_shape: S
 
 
 def detect_seamless(slab, held: Sequence[Range], global_shape: Sequence[int],
-                    channel: int = 0, group=None, tile_yx: Optional[Sequence[int]] = None):
+                    channel: int = 0, group=None, tile_yx: Optional[Sequence[int]] = None,
+                    ext_out: Optional[torch.Tensor] = None):
     """Detect blobs as if the whole volume were ONE chunk (no chunk seams).
 
     Each rank: exchange halo planes, run the fused chunk driver on its extended
@@ -713,7 +739,9 @@ def detect_seamless(slab, held: Sequence[Range], global_shape: Sequence[int],
     candidates (device to device, one batch of NCCL send/recv) and run
     ``_prune_blobs`` once over all of them (``mmb_prune_within``: cell-bucketed
     pair search, any listing order).  ``tile_yx`` additionally tiles y and x inside
-    a rank (tile + halo must fit the workspace of eight float volumes).
+    a rank (tile + halo must fit the workspace of eight float volumes).  ``ext_out``:
+    preallocated room for this rank's slab plus halo (``seamless_plan``'s extended
+    range) of which ``slab`` is already the owned view - see ``exchange_planes``.
 
     Returns on rank 0 the ``(n, 11)`` blob table of ``detector.detect_blobs`` in
     ``peak_local_max`` order (None if empty), None elsewhere.
@@ -723,7 +751,7 @@ def detect_seamless(slab, held: Sequence[Range], global_shape: Sequence[int],
     Z, Y, X = (int(v) for v in global_shape[:3])
     own, ext_ranges = seamless_plan(Z, world, bd[0], halo)
     # the caller's slabs need not coincide with the block-aligned owned slabs
-    ext = exchange_planes(slab, held, ext_ranges, group)
+    ext = exchange_planes(slab, held, ext_ranges, group, out=ext_out)
     mine = seamless_candidates(ext, ext_ranges[rank], own[rank], (Z, Y, X), channel, tile_yx)
     del ext
     parts = gather_tensor_rows(mine, 5, group, dtype=torch.int32, device=mine.device)

@@ -349,6 +349,51 @@ def test_preprocess_anisotropic_blocks(gpu):
     assert np.max(np.abs(out[:, :, :60].cpu().numpy() - want)) < 2e-5
 
 
+
+@pytest.mark.parametrize("shape,block,dtype", [
+    ((40, 90, 70), (40, 45, 35), np.uint16),      # every side above the one-CTA limit
+    ((37, 50, 64), (33, 50, 64), np.uint16),      # ragged trailing layer (4 planes)
+    ((20, 66, 41), (25, 33, 64), np.uint8),       # mixed: z and x clipped to the volume
+    ((34, 40, 40), (34, 40, 40), np.float32),     # one block, float keys
+    ((12, 70, 35), (2000, 2000, 2000), np.float64),   # `lowres`: block = chunk
+])
+def test_preprocess_large_blocks(gpu, shape, block, dtype):
+    """Blocks above 32 voxels a side (global-memory path, preprocess_large.cu): radix-select
+    percentiles, per-block 65-tap 'nearest' blur, block-mean erosion switch."""
+    vol, _ = synth.make_volume(shape, seed=23, density=1 / 1200.0)
+    nm = synth.near_max_of(vol)
+    if dtype == np.uint8:
+        vol = (vol >> 8).astype(np.uint8)
+        nm = nm / 256.0
+    elif dtype != np.uint16:
+        vol = (vol / 65535.0).astype(dtype)
+        nm = nm / 65535.0
+    prof = mm.Profile()
+    want = mm.preprocess_blocks(vol, block, prof, nm)
+    out = gpu.preprocess_blocks(gpu.as_source(vol), block, _params(gpu, prof, nm))
+    torch.cuda.synchronize()
+    got = out[:, :, :shape[2]].cpu().numpy()
+    err = np.max(np.abs(got - want))
+    print(f"large-block preprocess {shape} / {block} {np.dtype(dtype).name}: max abs err {err:.3e}")
+    assert err < 2e-5
+
+
+def test_preprocess_large_eroded_and_degenerate(gpu):
+    """A bright block (mean above erosion_threshold -> octahedron erosion inside the block
+    only) next to a constant block (vmin == vmax -> passed through unstretched)."""
+    rng = np.random.default_rng(5)
+    vol = np.zeros((40, 40, 80), dtype=np.uint16)
+    vol[:, :, :40] = rng.integers(20000, 60000, size=(40, 40, 40))
+    vol[:, :, 40:] = 1234
+    prof = mm.Profile()
+    want = mm.preprocess_blocks(vol, (40, 40, 40), prof, 30000.0)
+    out = gpu.preprocess_blocks(gpu.as_source(vol), (40, 40, 40), _params(gpu, prof, 30000.0))
+    torch.cuda.synchronize()
+    got = out[:, :, :80].cpu().numpy()
+    assert np.mean(mm.saturate_roi(vol[:, :, :40], prof, 30000.0)) > prof.erosion_threshold
+    scale = np.maximum(np.abs(want), 1.0)
+    assert np.max(np.abs(got - want) / scale) < 2e-5
+
 # ------------------------------------------------------------- fused driver
 
 def _blob_sets(cands, sigmas):
@@ -401,6 +446,21 @@ def test_detect_chunk_preprocessed(gpu):
     got, _ = det.detect(gpu.as_source(vol), res.sigmas, 0.1, 0.5, pre=_params(gpu, prof, nm),
                         block_shape=(25, 25, 25))
     _compare_detection(got, res, 0.1, "preprocessed 55x130x105")
+
+
+def test_detect_chunk_whole_chunk_block(gpu):
+    """`lowres`-style profile inside the fused chunk driver: the preprocessing block is the
+    whole chunk, so the large-block path runs in the sweep buffers the driver lends it."""
+    shape = (45, 100, 90)
+    vol, _ = synth.make_volume(shape, seed=8, density=1 / 3000.0)
+    nm = synth.near_max_of(vol)
+    prof = mm.Profile()
+    pre = mm.preprocess_blocks(vol, (2000, 2000, 2000), prof, nm)
+    res = ski.blob_log(pre, 3, 5, 10, 0.1, 0.5, full=True)
+    det = gpu.ChunkDetector(shape)
+    got, _ = det.detect(gpu.as_source(vol), res.sigmas, 0.1, 0.5, pre=_params(gpu, prof, nm),
+                        block_shape=(2000, 2000, 2000))
+    _compare_detection(got, res, 0.1, "whole-chunk block 45x100x90")
 
 
 def test_detect_chunk_overflow_regrows(gpu):
