@@ -2,16 +2,30 @@
 """Benchmark of the blob-detection hot path (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--config 2|3] [--mode chunks|seamless]
 
 One step = one pass of ``detect_blobs_blocks`` (chunked preprocessing, 10-scale
 LoG, 4-D local maxima, overlap pruning, seam pruning) over one synthetic
-cleared-tissue stack.  N=1 runs BASELINE config 2, 512x2048x2048 uint16 with
-the ``roi_blobs`` profile at 1 um isotropic resolution (50 chunks).  N>1 runs
-one such stack per GPU as the z-slabs of ONE N*512-plane volume (multi_gpu.detect_blobs_blocks_slabs).
+cleared-tissue stack.
+
+* ``--config 2`` (default; BASELINE ``configs[1]``): 512x2048x2048 uint16, ``roi_blobs``
+  profile, 1 um isotropic, 50 chunks of 500^3 (+5 overlap).  N > 1 runs one such stack
+  per GPU as the z-slabs of ONE N*512-plane volume (weak scaling,
+  ``multi_gpu.detect_blobs_blocks_slabs``).
+* ``--config 3`` (BASELINE ``configs[2]``): ONE 2048x8192x8192 uint16 volume sharded as
+  N z-slabs (``--shape`` shrinks it for fewer GPUs), chunk-faithful
+  (``--mode chunks``) or as one seamless chunk (``--mode seamless``,
+  ``multi_gpu.detect_seamless``).
+
+The volume is a pure function of (seed, z, y, x) generated on the device
+(``synth.device_volume``), so every rank's slab, the single-GPU re-run and the boxes the
+oracle recomputes are the same voxels.
 
 Prints ONE JSON line (rank 0).  ``value`` = GVoxel/s with the stack resident in
 HBM; ``e2e`` = the same through the public API from pinned HOST memory,
-host->device copy and result read-back inside the timed region.
+host->device copy and result read-back inside the timed region; ``config.parity`` =
+the blob table of the TIMED stack against the CPU oracle on sub-boxes (F1, unexplained
+differences) and, for N > 1, against the single-GPU table of the same volume.
 ``--impl reference`` times the CPU oracle (the reference algorithm restated on
 scipy, multiprocessing pool over chunks) on a bounded sample instead.
 """
@@ -31,54 +45,12 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SHAPE_FULL = (512, 2048, 2048)
+SHAPES = {2: (512, 2048, 2048), 3: (2048, 8192, 8192)}
 RESOLUTION = (1.0, 1.0, 1.0)
 SEED = 1
 METRIC = "blob_detection_throughput"
 UNIT = "GVoxel/s"
-
-
-# ----------------------------------------------------------------------------
-# synthetic input, generated on the device (same recipe as synth.make_volume)
-# ----------------------------------------------------------------------------
-
-def make_device_volume(shape, seed, device, z_offset=0, z_total=None):
-    """uint16 nuclei volume as an int16-bit tensor (torch has no full uint16).
-    Background N(400, 30), Gaussian nuclei sigma U(2.5, 4.5), amplitude
-    U(0.3, 0.9) * 65535, one per 6.7 k voxels.  Built in float32 plane batches."""
-    import torch
-    Z, Y, X = shape
-    g = torch.Generator(device=device)
-    g.manual_seed(seed * 7919 + z_offset)
-    vol = torch.empty((Z, Y, X), dtype=torch.float32, device=device)
-    for z0 in range(0, Z, 64):
-        z1 = min(Z, z0 + 64)
-        vol[z0:z1].normal_(400.0, 30.0, generator=g)
-    n = max(1, int(round(Z * Y * X / 6700.0)))
-    ctr = torch.rand((n, 3), generator=g, device=device) * torch.tensor(
-        [Z, Y, X], device=device, dtype=torch.float32)
-    sig = torch.rand(n, generator=g, device=device) * 2.0 + 2.5
-    amp = (torch.rand(n, generator=g, device=device) * 0.6 + 0.3) * 65535.0
-    R = 16
-    ax = torch.arange(-R, R + 1, device=device)
-    dz, dy, dx = torch.meshgrid(ax, ax, ax, indexing="ij")
-    offs = torch.stack([dz.reshape(-1), dy.reshape(-1), dx.reshape(-1)], dim=1)  # (K,3)
-    flat = vol.view(-1)
-    B = 192
-    for i in range(0, n, B):
-        c = ctr[i:i + B]
-        base = c.floor().long()
-        pos = base[:, None, :] + offs[None, :, :]                       # (b,K,3)
-        ok = ((pos >= 0) & (pos < torch.tensor([Z, Y, X], device=device))).all(-1)
-        d2 = ((pos.float() - c[:, None, :]) ** 2).sum(-1)
-        val = amp[i:i + B, None] * torch.exp(-0.5 * d2 / (sig[i:i + B, None] ** 2))
-        lin = (pos[..., 0] * Y + pos[..., 1]) * X + pos[..., 2]
-        flat.index_add_(0, lin[ok], val[ok])
-    vol.clamp_(0, 65535).round_()
-    out = vol.to(torch.int32)
-    del vol
-    out = torch.where(out > 32767, out - 65536, out).to(torch.int16)     # uint16 bit pattern
-    return out
+CORE = 96          # edge of the boxes the oracle recomputes for ``config.parity``
 
 
 def near_max_device(vol_i16):
@@ -174,20 +146,132 @@ def peaks_json():
 # CPU baseline (oracle = the reference algorithm restated on scipy)
 # ----------------------------------------------------------------------------
 
-def cpu_sample_shape(cores):
-    """About 10-30 s of CPU work at ~0.3 MVoxel/s/core, in 64-plane chunks."""
-    target = 0.3e6 * cores * 15.0
-    side = int(max(128, min(1024, (target / 128) ** 0.5)) // 64 * 64)
-    return (128, side, side)
+def cpu_sample_shape(cores, shape):
+    """The first P planes of the stack (up to 2048 x 2048 of each), P sized for about
+    20 s of CPU work at ~0.7 MVoxel/s/core (measured on the GPU box's host).  The reference's own chunking
+    (segment_size 500, overlap 5) then cuts it into up to 25 chunks of P x 505 x 505."""
+    y, x = min(shape[1], 2048), min(shape[2], 2048)
+    target = 0.7e6 * cores * 20.0
+    p = int(max(16, min(shape[0], round(target / (y * x)))))
+    return (p, y, x)
 
 
 def run_cpu_baseline(sample, near_max, cores):
     from oracle import magmap_restated as mm
-    prof = mm.Profile(segment_size=64)          # 64^3 chunks (+5 overlap): many tasks per core
+    prof = mm.Profile()                       # roi_blobs: 500-voxel chunks, 5 overlap
     t0 = time.perf_counter()
     blobs = mm.detect_blobs_blocks(sample, prof, RESOLUTION, near_max, processes=cores)
     dt = time.perf_counter() - t0
-    return sample.size / dt / 1e9, dt, 0 if blobs is None else len(blobs)
+    blocks = mm.setup_blocks(prof, sample.shape, RESOLUTION)
+    return sample.size / dt / 1e9, dt, 0 if blobs is None else len(blobs), \
+        int(np.prod(blocks.sub_roi_slices.shape))
+
+
+# ----------------------------------------------------------------------------
+# parity of the timed stack against the oracle (outside every timed region)
+# ----------------------------------------------------------------------------
+
+def _fetcher(device):
+    """Boxes of the timed volume regenerated on the device (a pure function of the
+    global coordinates) and copied to the host."""
+    from magellanmapper_b200 import synth
+
+    def fetch(z0, z1, y0, y1, x0, x1):
+        box = synth.device_volume((z1 - z0, y1 - y0, x1 - x0), SEED, offset=(z0, y0, x0),
+                                  device=device)
+        return box.cpu().numpy().view(np.uint16)
+    return fetch
+
+
+def parity_single_gpu(vol, shape, near_max, final_blobs, device, cores):
+    """Config 2 on one GPU: oracle recomputation of five cores (volume corner, chunk
+    interior, a chunk's high faces next to three seams, two boxes in the thin trailing
+    chunks) plus the oracle's seam pruning of the GPU's per-chunk tables at full size
+    against the GPU's final table (``oracle.subbox_check.check_stack``)."""
+    from oracle import magmap_restated as mm
+    from oracle import subbox_check as sb
+    from magellanmapper_b200.cv import stack_detect
+    from magellanmapper_b200.settings import config
+    settings = config.get_roi_profile(0)
+    blocks = stack_detect.setup_blocks(settings, shape)
+    seg_rois = stack_detect.StackDetector.detect_blobs_sub_rois(
+        None, vol, blocks.sub_roi_slices, blocks.sub_rois_offsets, blocks.denoise_max_shape,
+        blocks.exclude_border, False, [0])
+    out = sb.check_stack(_fetcher(device), shape, mm.Profile(), RESOLUTION, near_max, seg_rois,
+                         final_blobs, processes=min(cores, 5), core_size=CORE)
+    out.pop("box_results", None)
+    return out
+
+
+def parity_cores_global(final_rows, gshape, near_max, device, cores, seamless):
+    """Configs sharded over ranks: oracle recomputation of cores of the WHOLE volume
+    against rank 0's final table.  Seamless: the volume is one chunk, any box will do.
+    Chunk-faithful: cores at least 12 voxels from every inner chunk face, where the final
+    table is the chunk's own table (seam pruning only touches the overlap zones)."""
+    from oracle import magmap_restated as mm
+    from oracle import subbox_check as sb
+    prof = mm.Profile()
+    fetch = _fetcher(device)
+    blocks = mm.setup_blocks(prof, gshape, RESOLUTION)
+    grid = blocks.sub_roi_slices.shape
+    size = CORE
+    jobs = []
+    if seamless:
+        Z, Y, X = gshape
+        places = [((0, size), (0, size), (0, size)),
+                  tuple((n // 2 - size // 2, n // 2 - size // 2 + size) for n in gshape),
+                  ((Z - size, Z), (Y // 3, Y // 3 + size), (X - size, X)),
+                  ((Z // 4, Z // 4 + size), (Y - size, Y), (X // 5, X // 5 + size))]
+        for core in places:
+            core = tuple((max(0, a), min(n, b)) for (a, b), n in zip(core, gshape))
+            region = sb.plan_region(core, gshape, prof, RESOLUTION, blocks.denoise_max_shape)
+            raw = fetch(*[v for r in region for v in r])
+            rows = _rows_in(final_rows, region, (0, 0, 0))
+            jobs.append((raw, gshape, core, rows, prof, RESOLUTION, near_max,
+                         blocks.denoise_max_shape))
+    else:
+        last = tuple(g - 1 for g in grid)
+        picks = [((0, 0, 0), ("lo", "lo", "lo")), ((0, 0, 0), ("mid", "mid", "mid")),
+                 (tuple(min(1, g - 1) for g in grid), ("mid", "lo+", "mid")),
+                 (last, ("hi", "hi", "hi")),
+                 ((grid[0] // 2, last[1], grid[2] // 2), ("mid", "hi", "mid"))]
+        margin = 12
+        for coord, place in picks:
+            sl = blocks.sub_roi_slices[coord]
+            o = [s.start for s in sl]
+            cs = tuple(s.stop - s.start for s in sl)
+            core = []
+            for ax, (n, where) in enumerate(zip(cs, place)):
+                inner_lo = coord[ax] > 0                 # low face is a seam
+                inner_hi = coord[ax] < grid[ax] - 1      # high face is a seam
+                a_min = margin if inner_lo else 0
+                b_max = n - margin if inner_hi else n
+                w = min(size, max(1, b_max - a_min))
+                lo = {"lo": a_min, "lo+": a_min, "mid": max(a_min, (n - w) // 2),
+                      "hi": b_max - w}[where]
+                core.append((lo, lo + w))
+            region = sb.plan_region(core, cs, prof, RESOLUTION, blocks.denoise_max_shape)
+            raw = fetch(o[0] + region[0][0], o[0] + region[0][1], o[1] + region[1][0],
+                        o[1] + region[1][1], o[2] + region[2][0], o[2] + region[2][1])
+            rows = _rows_in(final_rows, [(a + oo, b + oo) for (a, b), oo in zip(region, o)], o)
+            jobs.append((raw, cs, tuple(core), rows, prof, RESOLUTION, near_max,
+                         blocks.denoise_max_shape))
+    results = sb.check_cores(jobs, processes=min(cores, len(jobs)))
+    return sb.summarize(results)
+
+
+def _rows_in(final_rows, box, origin):
+    """Rows ``z, y, x, radius`` of a final table inside the absolute ``box``, shifted to
+    be relative to ``origin``."""
+    if final_rows is None or len(final_rows) == 0:
+        return None
+    t = np.asarray(final_rows)
+    m = np.ones(len(t), dtype=bool)
+    for ax, (a, b) in enumerate(box):
+        m &= (t[:, ax] >= a) & (t[:, ax] < b)
+    rows = np.array(t[m][:, :4], dtype=np.float64)
+    rows[:, :3] -= np.asarray(origin, dtype=np.float64)
+    return rows
 
 
 # ----------------------------------------------------------------------------
@@ -198,15 +282,21 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--shape", type=str, default=None, help="z,y,x override (testing)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3])
+    ap.add_argument("--mode", default="chunks", choices=["chunks", "seamless"])
+    ap.add_argument("--shape", type=str, default=None,
+                    help="z,y,x override: per GPU for config 2, the whole volume for config 3")
+    ap.add_argument("--tile", type=str, default="2050,2050",
+                    help="seamless mode: y,x (or z,y,x) voxels of owned volume per tile")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-parity", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    shape = tuple(int(v) for v in args.shape.split(",")) if args.shape else SHAPE_FULL
+    shape = tuple(int(v) for v in args.shape.split(",")) if args.shape else SHAPES[args.config]
     cores = os.cpu_count() or 1
 
     if args.impl == "reference":
@@ -215,7 +305,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from magellanmapper_b200 import gpu, _lib
+    from magellanmapper_b200 import gpu, _lib, multi_gpu, synth
     from magellanmapper_b200.cv import stack_detect
     from magellanmapper_b200.io import np_io
 
@@ -229,34 +319,57 @@ def main():
     tmp = tempfile.mkdtemp(prefix="mmb_bench_")
     os.chdir(tmp)
 
-    # ---- input: one config-2 stack per rank (weak scaling) -----------------
-    vol = make_device_volume(shape, SEED + rank, device)
+    # ---- input: this rank's z-slab of the global volume --------------------------------
+    seamless = args.mode == "seamless"
+    if args.config == 2:
+        gshape = (shape[0] * world, shape[1], shape[2])        # weak: one stack per GPU
+    else:
+        gshape = shape                                         # one volume, N slabs
+    held = multi_gpu.slab_bounds(gshape[0], world)
+    z0, z1 = held[rank]
+    ext_out = None
+    if seamless:
+        # room for the halo around the slab, generated in place (a second copy of a
+        # whole-brain slab would not fit next to the first)
+        settings_probe = setup_config(1.0, os.path.join(tmp, "probe"))
+        _, _, _, halo, bd = multi_gpu._seamless_setup(gshape, 0)
+        own, ext_ranges = multi_gpu.seamless_plan(gshape[0], world, bd[0], halo)
+        held = own
+        z0, z1 = held[rank]
+        e0, e1 = ext_ranges[rank]
+        ext_out = torch.empty((e1 - e0, gshape[1], gshape[2]), dtype=torch.int16, device=device)
+        vol = ext_out[z0 - e0:z1 - e0]
+        synth.device_volume(vol.shape, SEED, offset=(z0, 0, 0), device=device, out=vol)
+    else:
+        vol = synth.device_volume((z1 - z0, gshape[1], gshape[2]), SEED, offset=(z0, 0, 0),
+                                  device=device)
     near_max = near_max_device(vol)
     if world > 1:
         t = torch.tensor([near_max], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         near_max = float(t.item())
     setup_config(near_max, os.path.join(tmp, f"bench_r{rank}"))
-    img5d_dev = np_io.Image5d(vol[None])
-    nvox = float(np.prod(shape))
-
-    # N > 1: the ranks' stacks are the z-slabs of ONE world*Z-plane volume.  The
-    # reference's chunk grid is laid over the whole volume, chunk rows are dealt to
-    # the slab holding their first plane, missing planes arrive by NCCL send/recv
-    # (halo exchange), tables are gathered to rank 0 and seam-pruned there.
-    from magellanmapper_b200 import multi_gpu
-    held = multi_gpu.slab_bounds(shape[0] * world, world)
-    gshape = (shape[0] * world, shape[1], shape[2])
+    nvox_global = float(np.prod(gshape))
+    tile = tuple(int(v) for v in args.tile.split(","))
 
     def step_resident():
+        if seamless:
+            table = multi_gpu.detect_seamless(vol, held, gshape, 0, tile_yx=tile,
+                                              ext_out=ext_out)
+            return table
         if world == 1:
             _, _, blobs = stack_detect.detect_blobs_blocks(
-                os.path.join(tmp, f"bench_r{rank}"), img5d_dev, None, None, [0], False, False,
-                True)
+                os.path.join(tmp, f"bench_r{rank}"), np_io.Image5d(vol[None]), None, None, [0],
+                False, False, True)
         else:
             _, _, blobs = multi_gpu.detect_blobs_blocks_slabs(
                 os.path.join(tmp, f"bench_r{rank}"), vol, held, gshape, [0])
         return blobs
+
+    def table_of(res):
+        if res is None:
+            return None
+        return res if isinstance(res, np.ndarray) else res.blobs
 
     def barrier():
         torch.cuda.synchronize()
@@ -266,7 +379,41 @@ def main():
 
     lib.mmb_profile_enable(1)          # warm the library's event pool as well
     for _ in range(args.warmup):
-        step_resident()
+        res = step_resident()
+    lib.mmb_profile_enable(0)
+
+    # ---- parity of this very stack (before timing; nothing of it is timed) -------------
+    parity = None
+    if not args.skip_parity:
+        final = table_of(res)
+        t_par = time.perf_counter()
+        if world > 1 and args.config == 2 and not seamless:
+            barrier()
+            if rank == 0:
+                whole = synth.device_volume(gshape, SEED, device=device)
+                _, _, one = stack_detect.detect_blobs_blocks(
+                    os.path.join(tmp, "single"), np_io.Image5d(whole[None]), None, None, [0],
+                    False, False, True)
+                del whole
+                same = (one.blobs is not None and final is not None
+                        and one.blobs.shape == final.shape
+                        and bool(np.array_equal(one.blobs, final)))
+                parity = {"multi_gpu_table_equals_single_gpu_table": same,
+                          "rows": 0 if final is None else int(len(final)),
+                          "rows_single_gpu": 0 if one.blobs is None else int(len(one.blobs))}
+                if not same:
+                    raise SystemExit(f"parity: the {world}-rank table differs from the "
+                                     f"single-GPU table of the same volume: {parity}")
+                stack_detect.StackDetector.release_workspace()
+            barrier()
+        if rank == 0:
+            if world == 1 and not seamless:
+                p = parity_single_gpu(vol, gshape, near_max, final, device, cores)
+            else:
+                p = parity_cores_global(final, gshape, near_max, device, cores, seamless)
+            parity = dict(parity or {}, **p)
+            parity["seconds"] = round(time.perf_counter() - t_par, 1)
+        barrier()
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -278,15 +425,16 @@ def main():
     t0 = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
-        blobs = step_resident()
+        res = step_resident()
     ev1.record()
     barrier()
     wall = time.perf_counter() - t0
     dev_ms = ev0.elapsed_time(ev1)
     launches = lib.mmb_launch_count() - launches0
-    n_blobs = 0 if blobs is None or blobs.blobs is None else len(blobs.blobs)
-    stage_times = None if blobs is None or not getattr(blobs, "times", None) else {
-        k.value: round(float(v[0]), 4) for k, v in blobs.times.items()}
+    final = table_of(res)
+    n_blobs = 0 if final is None else len(final)
+    stage_times = None if res is None or not getattr(res, "times", None) else {
+        k.value: round(float(v[0]), 4) for k, v in res.times.items()}
     import ctypes as C
     ms = (C.c_double * 10)(); cnt = (C.c_int64 * 10)(); units = (C.c_double * 10)()
     lib.mmb_profile_collect(ms, cnt, units)
@@ -300,11 +448,22 @@ def main():
         tt = torch.tensor([t_step], device=device, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_step = float(tt.item())
-    value = nvox * world * args.steps / t_step / 1e9
+    value = nvox_global * args.steps / t_step / 1e9
 
     # ---- e2e: pinned host stack -> public API -> blob table on the host ----
     e2e = None
-    if not args.skip_e2e:
+    slab_bytes = int(np.prod(vol.shape)) * 2
+    do_e2e = not args.skip_e2e and not seamless
+    if do_e2e:
+        import psutil
+        # every rank pins its slab; leave the host comfortable head-room
+        if slab_bytes * world * 1.5 > psutil.virtual_memory().available:
+            do_e2e = False
+    if world > 1:
+        tt = torch.tensor([int(do_e2e)], device=device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MIN)
+        do_e2e = bool(tt.item())
+    if do_e2e:
         host = torch.empty(vol.shape, dtype=torch.int16).pin_memory()
         host.copy_(vol)
         torch.cuda.synchronize()
@@ -340,8 +499,10 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             nb_e2e = int(tt.item())
         d2h = nb_e2e * 8 * 8          # final table: 8 float64 columns per blob
-        e2e = {"value": nvox * world * args.steps / t_e2e / 1e9, "unit": UNIT,
-               "h2d_bytes_per_step": int(nvox * 2) * world, "d2h_bytes_per_step": d2h}
+        e2e = {"value": nvox_global * args.steps / t_e2e / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": int(nvox_global * 2), "d2h_bytes_per_step": d2h}
+        if final is not None and b is not None and b.blobs is not None:
+            e2e["table_equals_resident"] = bool(np.array_equal(b.blobs, final))
         del host, host_np, img5d_host
 
     if rank != 0:
@@ -365,15 +526,18 @@ def main():
     # DRAM traffic of the dominant kernel from the committed ncu capture (bytes per
     # voxel measured on one 505^3 chunk), scaled to this run's average launch size
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic_v10.json")
-    if os.path.exists(tpath):
+    for name in ("r02_traffic.json", "r01_traffic_v10.json"):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(tpath):
+            continue
         with open(tpath) as f:
             tj = json.load(f)
         if dom in tj["kernels"]:
             vox_per_launch = units[kinds.index(dom)] / per_kind[dom]["launches"]
             traffic = tj["kernels"][dom]["dram_bytes_per_voxel"] * vox_per_launch
-            traffic_src = ("dram__bytes_read.sum + dram__bytes_write.sum per voxel from "
-                           "profiles/r01_traffic_v10.json x this run's voxels per launch")
+            traffic_src = (f"dram__bytes_read.sum + dram__bytes_write.sum per voxel from "
+                           f"profiles/{name} x this run's voxels per launch")
+            break
     roof = {"bound": "hbm", "kernel": dom, "achieved": per_kind[dom]["gbps"],
             "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": per_kind[dom]["gbps"] / peaks["hbm_gbs"], "traffic": traffic,
@@ -383,6 +547,7 @@ def main():
             "peak_source": f"{peak_src} copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
             "avg_launch_ms": per_kind[dom]["ms"] / per_kind[dom]["launches"],
             "algorithmic_bytes_per_voxel": alg_bytes[dom],
+            "units": "true voxels (X, not the padded row pitch) of rank 0's launches",
             "fp32_colimit": "the three sweeps execute (14 r + 7) fp32 FMAs per voxel per scale "
                             "(r = 12..20) as packed FFMA2; at the 128 lane-FMA/clk/SM pipe peak "
                             "that alone takes as long as moving the algorithmic bytes at the "
@@ -391,32 +556,46 @@ def main():
 
     cpu = None
     if not args.skip_cpu:
-        sshape = cpu_sample_shape(cores)
-        sshape = tuple(min(a, b) for a, b in zip(sshape, shape))
+        sshape = cpu_sample_shape(cores, vol.shape)
         sample = vol[:sshape[0], :sshape[1], :sshape[2]].cpu().numpy().view(np.uint16)
-        gv, dt, nb = run_cpu_baseline(np.ascontiguousarray(sample), near_max, cores)
+        gv, dt, nb, nchunks = run_cpu_baseline(np.ascontiguousarray(sample), near_max, cores)
         cpu = {"value": gv, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{sshape[0]}x{sshape[1]}x{sshape[2]} corner of the same stack, "
-                         f"64^3-voxel chunks, fork pool of {cores} processes, {dt:.1f} s, "
+               "sample": f"first {sshape[0]} planes x {sshape[1]} x {sshape[2]} of the timed "
+                         f"stack, the reference's own chunking (segment_size 500, overlap 5: "
+                         f"{nchunks} chunks), fork pool of {cores} processes, {dt:.1f} s, "
                          f"{nb} blobs"}
 
+    if args.config == 2:
+        workload = (f"BASELINE config 2: synthetic cleared-tissue stack "
+                    f"{shape[0]}x{shape[1]}x{shape[2]} uint16 per GPU, roi_blobs "
+                    f"profile, detect_blobs_blocks (25^3 block preprocessing, 10-scale "
+                    f"LoG sigma 3..5, 4-D local maxima, overlap + seam pruning), "
+                    f"chunk-faithful, 500^3-voxel chunks with 5-voxel overlap")
+    else:
+        workload = (f"BASELINE config 3: synthetic whole-brain volume "
+                    f"{gshape[0]}x{gshape[1]}x{gshape[2]} uint16 as {world} z-slabs, roi_blobs "
+                    f"profile, " + ("ONE seamless chunk (halo exchange, local maxima per slab "
+                                    f"tile of {tile}, one global overlap pruning on rank 0)"
+                                    if seamless else
+                                    "chunk-faithful detect_blobs_blocks (500^3-voxel chunks, "
+                                    "5-voxel overlap, seam pruning)"))
+    multi = None
+    if world > 1:
+        multi = (f"{world} z-slabs of one {gshape[0]}x{gshape[1]}x{gshape[2]} volume, "
+                 + ("halo planes by NCCL send/recv, candidates gathered to rank 0 and pruned "
+                    "there once" if seamless else
+                    "chunk rows dealt in balanced runs (single row x y-column units lent "
+                    "between ranks), halo planes and lent sub-boxes by NCCL send/recv, device "
+                    "tables gathered to rank 0 and seam-pruned there"))
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t_step / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": f"BASELINE config 2: synthetic cleared-tissue stack "
-                               f"{shape[0]}x{shape[1]}x{shape[2]} uint16 per GPU, roi_blobs "
-                               f"profile, detect_blobs_blocks (25^3 block preprocessing, 10-scale "
-                               f"LoG sigma 3..5, 4-D local maxima, overlap + seam pruning), "
-                               f"chunk-faithful, 500^3-voxel chunks with 5-voxel overlap",
+        "higher_is_better": True, "scaling": "weak" if args.config == 2 else "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload,
                    "l2": "inputs larger than L2 (every sweep streams >= 1 GB per launch)",
                    "blobs_per_step": n_blobs, "host_stage_s_last_step": stage_times,
-                   "multi_gpu": None if world == 1 else
-                   f"{world} z-slabs of one {gshape[0]}x{gshape[1]}x{gshape[2]} volume, chunk rows "
-                   f"dealt in balanced runs (single row x y-column units lent between ranks), "
-                   f"halo planes and lent sub-boxes by NCCL send/recv, device tables gathered "
-                   f"to rank 0 and seam-pruned there"},
+                   "multi_gpu": multi, "parity": parity},
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
         "clocks": clocks,
     }
@@ -428,27 +607,30 @@ def main():
 def run_reference(args, rank, world, shape, cores):
     """Reference arm: the reference's CPU algorithm (oracle port; scikit-image is
     not installable here) with a fork pool over all host cores, on a bounded
-    sample of the same workload."""
+    sample of the same workload, cut by the reference's own chunking."""
     if rank != 0:
         return
     from magellanmapper_b200 import synth
-    sshape = tuple(min(a, b) for a, b in zip(cpu_sample_shape(cores), shape))
+    sshape = cpu_sample_shape(cores, shape)
     sample, _ = synth.make_volume(sshape, SEED)
     near_max = synth.near_max_of(sample)
     for _ in range(min(args.warmup, 1)):
         run_cpu_baseline(sample, near_max, cores)
-    t_tot, nb = 0.0, 0
+    t_tot, nb, nchunks = 0.0, 0, 0
     for _ in range(args.steps):
-        gv, dt, nb = run_cpu_baseline(sample, near_max, cores)
+        gv, dt, nb, nchunks = run_cpu_baseline(sample, near_max, cores)
         t_tot += dt
     value = sample.size * args.steps / t_tot / 1e9
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": min(args.warmup, 1),
-        "ms_per_step": t_tot / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": t_tot / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak" if args.config == 2 else "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"bounded sample {sshape[0]}x{sshape[1]}x{sshape[2]} of BASELINE "
-                               f"config 2 (same generator and profile), 64^3-voxel chunks"},
+        "config": {"workload": f"bounded sample of BASELINE config {args.config}: the first "
+                               f"{sshape[0]} planes x {sshape[1]} x {sshape[2]} of a stack of the "
+                               f"same recipe (numpy generator) and profile, the reference's own "
+                               f"chunking (segment_size 500, overlap 5: {nchunks} chunks)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{sshape[0]}x{sshape[1]}x{sshape[2]}, fork pool of {cores}, "
                                    f"{nb} blobs"},

@@ -90,8 +90,10 @@ static cudaEvent_t take_event() {
 }
 
 bool prof_enabled() { return g_prof_on.load(std::memory_order_relaxed); }
+static thread_local double t_unit_scale = 1.0;
+void prof_set_unit_scale(double f) { t_unit_scale = f; }
 void prof_begin(int kind, double units, cudaStream_t st) {
-  t_open.kind = kind; t_open.units = units;
+  t_open.kind = kind; t_open.units = units * t_unit_scale;
   t_open.a = take_event(); t_open.b = take_event();
   cudaEventRecord(t_open.a, st);
 }

@@ -104,6 +104,9 @@ enum ProfKind {
 bool prof_enabled();
 void prof_begin(int kind, double units, cudaStream_t st);
 void prof_end(cudaStream_t st);
+// units of the scopes opened by this thread are multiplied by `f` until reset to 1: the
+// sweeps work on pitch-padded rows but report TRUE voxels (X / pitch)
+void prof_set_unit_scale(double f);
 struct ProfScope {
   cudaStream_t st;
   bool on;

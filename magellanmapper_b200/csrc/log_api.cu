@@ -121,11 +121,17 @@ static int log_pass(const float* in0, const float* in1, float* out0, float* out1
                     !(axis == 2 && mode != MODE_FIRST);
   if (!fast)
     return run_generic(in0, in1, out0, out1, Z, Y, X, pitch, axis, mode, sigma, (float)scale, st);
-  if (axis == 2) return launch_x_first(r, in0, out0, out1, (int64_t)Z * Y, X, pitch, w, st);
-  if (axis == 1)
-    return launch_strided(mode, r, in0, in1, out0, out1, Y, pitch, Z, w, (float)scale, st);
-  return launch_strided(mode, r, in0, in1, out0, out1, Z, (int64_t)Y * pitch, 1, w,
+  // the sweeps see pitch-padded rows; the profile counts the true voxels
+  prof_set_unit_scale((double)X / (double)pitch);
+  int rc;
+  if (axis == 2) rc = launch_x_first(r, in0, out0, out1, (int64_t)Z * Y, X, pitch, w, st);
+  else if (axis == 1)
+    rc = launch_strided(mode, r, in0, in1, out0, out1, Y, pitch, Z, w, (float)scale, st);
+  else
+    rc = launch_strided(mode, r, in0, in1, out0, out1, Z, (int64_t)Y * pitch, 1, w,
                         (float)scale, st);
+  prof_set_unit_scale(1.0);
+  return rc;
 }
 
 int log_scale_impl(const float* in, float* out, float* work, int Z, int Y, int X, int64_t pitch,
