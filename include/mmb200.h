@@ -92,6 +92,25 @@ int mmb_to_float(const void* in, int dtype, const int64_t in_strides[3],
                  int Z, int Y, int X, float* out, int64_t pitch, double scale,
                  void* stream);
 
+/* ---- isotropic resize -------------------------------------------------------
+ * Replaces cv_nd.make_isotropic (magmap/cv/cv_nd.py:1071-1106, called from
+ * magmap/cv/detector.py:893-897), i.e. skimage.transform.resize(roi, out_shape,
+ * mode='reflect', preserve_range=True).astype(roi.dtype): Gaussian anti-aliasing on
+ * the axes that shrink (sigma = (in/out - 1)/2, truncate 4), then order-1
+ * scipy.ndimage.zoom(grid_mode=True), all in float64; integer dtypes are truncated
+ * back to integers.  `edge_mode`: 0 = 'reflect' (ndimage 'mirror'), 1 = 'edge'
+ * (ndimage 'nearest'; the reference's choice for ROIs one voxel thick).  The result
+ * is a pitched float32 volume [Zo][Yo][pitch_out].                                  */
+int mmb_resize_linear(const void* in, int dtype, const int64_t in_strides[3], int Z, int Y,
+                      int X, float* out, int Zo, int Yo, int Xo, int64_t pitch_out,
+                      int edge_mode, void* stream);
+
+/* ---- spectral unmixing ------------------------------------------------------
+ * One step of the loop at magmap/cv/detector.py:910-921:
+ * target = max(target - factor * other, 0) on two pitched float32 volumes.         */
+int mmb_unmix_subtract(float* target, const float* other, int Z, int Y, int X, int64_t pitch,
+                       double factor, void* stream);
+
 /* ---- saturate_roi + denoise_roi per preprocessing block --------------------
  * Replaces the loop at magmap/cv/stack_detect.py:122-150 that calls
  * plot_3d.saturate_roi (plot_3d.py:55-111) and plot_3d.denoise_roi

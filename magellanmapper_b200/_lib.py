@@ -75,6 +75,10 @@ SIGNATURES = {
     "mmb_preprocess_blocks": (C.c_int, [_vp, C.c_int, _I64x3, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_int, C.c_int,
                                         C.POINTER(MmbPreprocParams), _vp, C.c_int64, _vp]),
+    "mmb_resize_linear": (C.c_int, [_vp, C.c_int, _I64x3, C.c_int, C.c_int, C.c_int, _vp, C.c_int,
+                                    C.c_int, C.c_int, C.c_int64, C.c_int, _vp]),
+    "mmb_unmix_subtract": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int64,
+                                     C.c_double, _vp]),
     "mmb_log_work_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int64]),
     "mmb_log_scale": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int64,
                                 C.c_double, _vp]),
