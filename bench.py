@@ -121,17 +121,25 @@ class ClockSampler:
 # profile / config plumbing
 # ----------------------------------------------------------------------------
 
-def setup_config(near_max, filename):
+def setup_config(near_max, filename, resolution=RESOLUTION, channel_mods=None):
+    """``roi_blobs`` for every channel (``channel_mods``: one dict of profile overrides per
+    channel), resolution and the importer's ``near_max`` metadata."""
     from magellanmapper_b200.settings import config, roi_prof
-    prof = roi_prof.ROIProfile()
-    prof.add_profiles("roi_blobs.yaml")
-    config.roi_profile = prof
-    config.roi_profiles = [prof]
-    config.resolutions = [list(RESOLUTION)]
-    config.near_max = [near_max]
+    near_maxs = list(near_max) if isinstance(near_max, (list, tuple)) else [near_max]
+    profs = []
+    for c in range(len(near_maxs)):
+        prof = roi_prof.ROIProfile()
+        prof.add_profiles("roi_blobs.yaml")
+        for k, v in ((channel_mods or [{}] * len(near_maxs))[c]).items():
+            prof[k] = v
+        profs.append(prof)
+    config.roi_profile = profs[0]
+    config.roi_profiles = profs
+    config.resolutions = [list(resolution)]
+    config.near_max = near_maxs
     config.channel = None
     config.filename = filename
-    return prof
+    return profs[0]
 
 
 def peaks_json():
@@ -140,6 +148,64 @@ def peaks_json():
         with open(p) as f:
             return json.load(f), "measured"
     return {"hbm_gbs": 6650.0}, "fallback"
+
+
+KINDS = ["to_float", "preprocess", "log_x", "log_y", "log_z", "localmax", "prune_edges",
+         "prune_resolve", "compact", "seam_match"]
+ALG_BYTES = {"preprocess": 6.0, "log_x": 12.0, "log_y": 16.0, "log_z": 12.0, "localmax": 4.0}
+
+
+def collect_profile(lib):
+    import ctypes as C
+    ms = (C.c_double * 10)(); cnt = (C.c_int64 * 10)(); units = (C.c_double * 10)()
+    lib.mmb_profile_collect(ms, cnt, units)
+    lib.mmb_profile_enable(0)
+    return ms, cnt, units
+
+
+def roofline_block(ms, cnt, units):
+    """Roofline of the dominant kernel (the y sweep: 8 B in + 8 B out per voxel) from the
+    CUDA events the library records around every launch on the launching stream."""
+    peaks, peak_src = peaks_json()
+    kinds, alg_bytes = KINDS, ALG_BYTES
+    per_kind = {}
+    total_ms = sum(ms)
+    for i, k in enumerate(kinds):
+        if cnt[i]:
+            per_kind[k] = {"ms": ms[i], "launches": int(cnt[i]), "share": ms[i] / total_ms,
+                           "gbps": (alg_bytes[k] * units[i] / (ms[i] * 1e-3) / 1e9
+                                    if k in alg_bytes else None)}
+    dom = max((k for k in per_kind if k in alg_bytes), key=lambda k: per_kind[k]["ms"])
+    # DRAM traffic of the dominant kernel from the committed ncu capture (bytes per
+    # voxel measured on one 505^3 chunk), scaled to this run's average launch size
+    traffic, traffic_src = None, None
+    for name in ("r02_traffic.json", "r01_traffic_v10.json"):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(tpath):
+            continue
+        with open(tpath) as f:
+            tj = json.load(f)
+        if dom in tj["kernels"]:
+            vox_per_launch = units[kinds.index(dom)] / per_kind[dom]["launches"]
+            traffic = tj["kernels"][dom]["dram_bytes_per_voxel"] * vox_per_launch
+            traffic_src = (f"dram__bytes_read.sum + dram__bytes_write.sum per voxel from "
+                           f"profiles/{name} x this run's voxels per launch")
+            break
+    return {"bound": "hbm", "kernel": dom, "achieved": per_kind[dom]["gbps"],
+            "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": per_kind[dom]["gbps"] / peaks["hbm_gbs"], "traffic": traffic,
+            "traffic_source": traffic_src,
+            "algorithmic_bytes_per_launch": alg_bytes[dom] * units[kinds.index(dom)]
+            / per_kind[dom]["launches"],
+            "peak_source": f"{peak_src} copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
+            "avg_launch_ms": per_kind[dom]["ms"] / per_kind[dom]["launches"],
+            "algorithmic_bytes_per_voxel": alg_bytes[dom],
+            "units": "true voxels (X, not the padded row pitch) of rank 0's launches",
+            "fp32_colimit": "the three sweeps execute (14 r + 7) fp32 FMAs per voxel per scale "
+                            "(r = 12..20) as packed FFMA2; at the 128 lane-FMA/clk/SM pipe peak "
+                            "that alone takes as long as moving the algorithmic bytes at the "
+                            "measured HBM peak (DESIGN.md section 4)",
+            "per_kernel": per_kind}
 
 
 # ----------------------------------------------------------------------------
@@ -156,13 +222,13 @@ def cpu_sample_shape(cores, shape):
     return (p, y, x)
 
 
-def run_cpu_baseline(sample, near_max, cores):
+def run_cpu_baseline(sample, near_max, cores, prof=None, resolution=RESOLUTION):
     from oracle import magmap_restated as mm
-    prof = mm.Profile()                       # roi_blobs: 500-voxel chunks, 5 overlap
+    prof = prof or mm.Profile()               # roi_blobs: 500-voxel chunks, 5 overlap
     t0 = time.perf_counter()
-    blobs = mm.detect_blobs_blocks(sample, prof, RESOLUTION, near_max, processes=cores)
+    blobs = mm.detect_blobs_blocks(sample, prof, resolution, near_max, processes=cores)
     dt = time.perf_counter() - t0
-    blocks = mm.setup_blocks(prof, sample.shape, RESOLUTION)
+    blocks = mm.setup_blocks(prof, sample.shape, resolution)
     return sample.size / dt / 1e9, dt, 0 if blobs is None else len(blobs), \
         int(np.prod(blocks.sub_roi_slices.shape))
 
@@ -171,13 +237,13 @@ def run_cpu_baseline(sample, near_max, cores):
 # parity of the timed stack against the oracle (outside every timed region)
 # ----------------------------------------------------------------------------
 
-def _fetcher(device):
+def _fetcher(device, seed=SEED):
     """Boxes of the timed volume regenerated on the device (a pure function of the
     global coordinates) and copied to the host."""
     from magellanmapper_b200 import synth
 
     def fetch(z0, z1, y0, y1, x0, x1):
-        box = synth.device_volume((z1 - z0, y1 - y0, x1 - x0), SEED, offset=(z0, y0, x0),
+        box = synth.device_volume((z1 - z0, y1 - y0, x1 - x0), seed, offset=(z0, y0, x0),
                                   device=device)
         return box.cpu().numpy().view(np.uint16)
     return fetch
@@ -203,18 +269,19 @@ def parity_single_gpu(vol, shape, near_max, final_blobs, device, cores):
     return out
 
 
-def parity_cores_global(final_rows, gshape, near_max, device, cores, seamless):
+def parity_cores_global(final_rows, gshape, near_max, device, cores, seamless, prof=None,
+                        resolution=RESOLUTION, seed=SEED, size=CORE, max_boxes=5):
     """Configs sharded over ranks: oracle recomputation of cores of the WHOLE volume
     against rank 0's final table.  Seamless: the volume is one chunk, any box will do.
     Chunk-faithful: cores at least 12 voxels from every inner chunk face, where the final
     table is the chunk's own table (seam pruning only touches the overlap zones)."""
     from oracle import magmap_restated as mm
     from oracle import subbox_check as sb
-    prof = mm.Profile()
-    fetch = _fetcher(device)
+    RESOLUTION = resolution
+    prof = prof or mm.Profile()
+    fetch = _fetcher(device, seed)
     blocks = mm.setup_blocks(prof, gshape, RESOLUTION)
     grid = blocks.sub_roi_slices.shape
-    size = CORE
     jobs = []
     if seamless:
         Z, Y, X = gshape
@@ -236,7 +303,7 @@ def parity_cores_global(final_rows, gshape, near_max, device, cores, seamless):
                  (last, ("hi", "hi", "hi")),
                  ((grid[0] // 2, last[1], grid[2] // 2), ("mid", "hi", "mid"))]
         margin = 12
-        for coord, place in picks:
+        for coord, place in picks[:max_boxes]:
             sl = blocks.sub_roi_slices[coord]
             o = [s.start for s in sl]
             cs = tuple(s.stop - s.start for s in sl)
@@ -274,6 +341,201 @@ def _rows_in(final_rows, box, origin):
     return rows
 
 
+
+# ----------------------------------------------------------------------------
+# BASELINE configs 1, 4 and 5 (one GPU each)
+# ----------------------------------------------------------------------------
+
+NAMED = {
+    1: dict(shape=(50, 500, 500), resolution=(1.0, 1.0, 1.0), mods=[{}],
+            what="BASELINE config 1: synthetic 4x nuclei ROI uint16 zyx {shape}, single "
+                 "channel, roi_blobs profile, detector.detect_blobs (img_as_float, 10-scale "
+                 "LoG sigma 3..5, 4-D local maxima, overlap pruning) on the raw ROI"),
+    4: dict(shape=(1024, 4096, 4096), resolution=(1.0, 1.0, 1.0),
+            mods=[{}, {"min_sigma_factor": 4, "max_sigma_factor": 10}],
+            what="BASELINE config 4: two-channel synthetic volume {shape} uint16 "
+                 "(channel-last), per-channel profiles (sigma 3..5 and 4..10, num_sigma 10), "
+                 "both channels detected in ONE detect_blobs_stack pass; GVoxel counts every "
+                 "channel's voxels"),
+    5: dict(shape=(1024, 4096, 4096), resolution=(5.0, 1.0, 1.0), mods=[{}],
+            what="BASELINE config 5: scale-anisotropic volume {shape} uint16 at 5x1x1 um "
+                 "(chunks 101x505x505, preprocessing blocks 5x25x25, overlap 1x5x5), "
+                 "detect_blobs_stack with saturate + denoise preprocessing fused"),
+}
+
+
+def main_named(args, shape, cores):
+    """Configs 1, 4, 5 on one GPU, same JSON contract as the default run."""
+    import torch
+    from magellanmapper_b200 import gpu, _lib, synth
+    from magellanmapper_b200.cv import detector, stack_detect
+    from magellanmapper_b200.io import np_io
+    from oracle import magmap_restated as mm
+    cfg = NAMED[args.config]
+    res = cfg["resolution"]
+    n_chl = len(cfg["mods"])
+    torch.cuda.set_device(0)
+    device = torch.device("cuda", 0)
+    lib = _lib.load()
+    gpu.require_cuda()
+    tmp = tempfile.mkdtemp(prefix="mmb_bench_")
+    os.chdir(tmp)
+    seeds = [SEED + 100 * c for c in range(n_chl)]
+    if n_chl == 1:
+        vol = synth.device_volume(shape, seeds[0], device=device)
+        near_maxs = [near_max_device(vol)]
+    else:
+        vol = torch.empty(tuple(shape) + (n_chl,), dtype=torch.int16, device=device)
+        near_maxs = [0.0] * n_chl
+        for c in range(n_chl):
+            for z0 in range(0, shape[0], 64):
+                z1 = min(shape[0], z0 + 64)
+                part = synth.device_volume((z1 - z0, shape[1], shape[2]), seeds[c],
+                                           offset=(z0, 0, 0), device=device)
+                near_maxs[c] = max(near_maxs[c], near_max_device(part))
+                vol[z0:z1, :, :, c] = part
+            del part
+    setup_config(near_maxs, os.path.join(tmp, "bench"), res, cfg["mods"])
+    nvox = float(np.prod(shape)) * n_chl
+    chls = list(range(n_chl))
+
+    def run(img, base):
+        if args.config == 1:
+            return detector.detect_blobs(img, chls)
+        if isinstance(img, np.ndarray):
+            i5 = np_io.Image5d(img[None])
+            i5.is_roi = True
+            _, _, b = stack_detect.detect_blobs_stack(os.path.join(tmp, base), i5)
+        else:
+            _, _, b = stack_detect.detect_blobs_blocks(
+                os.path.join(tmp, base), np_io.Image5d(img[None]), None, None, chls, False,
+                False, True)
+        return None if b is None else b.blobs
+
+    lib.mmb_profile_enable(1)
+    for _ in range(args.warmup):
+        final = run(vol, "res")
+    lib.mmb_profile_enable(0)
+
+    parity = None
+    if not args.skip_parity:
+        t_par = time.perf_counter()
+        parts = []
+        for c in chls:
+            mods = {k: v for k, v in cfg["mods"][c].items()}
+            prof = mm.Profile(**mods)
+            rows = None if final is None else final[final[:, 6] == c]
+            wide = prof.max_sigma_factor > 6          # wide ladders need wide margins
+            if args.config == 1:
+                from oracle import subbox_check as sb
+                cores_ = [((0, shape[0]), (0, CORE), (0, CORE)),
+                          ((0, shape[0]), (shape[1] // 2, shape[1] // 2 + CORE),
+                           (shape[2] - CORE, shape[2]))]
+                fetch = _fetcher(device, seeds[c])
+                jobs = []
+                for core in cores_:
+                    region = sb.plan_region(core, shape, prof, res, None)
+                    # the ROI is one chunk: table rows are already chunk-relative
+                    jobs.append((fetch(*[v for r in region for v in r]), shape, core,
+                                 None if rows is None else rows[:, :4], prof, res, near_maxs[c],
+                                 None))
+                parts.append(sb.summarize(sb.check_cores(jobs, processes=min(cores, 2))))
+            else:
+                parts.append(parity_cores_global(
+                    rows, shape, near_maxs[c], device, cores, False, prof, res, seeds[c],
+                    48 if wide else CORE, 3 if wide else 5))
+        parity = {k: (sum(p[k] for p in parts) if k != "f1" else None) for k in parts[0]}
+        tp2 = sum(p["f1"] * (p["gpu_blobs"] + p["oracle_blobs"]) for p in parts)
+        parity["f1"] = tp2 / max(parity["gpu_blobs"] + parity["oracle_blobs"], 1)
+        parity["seconds"] = round(time.perf_counter() - t_par, 1)
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    launches0 = lib.mmb_launch_count()
+    lib.mmb_profile_enable(1)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        final = run(vol, "res")
+    ev1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    t_step = max(wall, ev0.elapsed_time(ev1) / 1e3)
+    launches = lib.mmb_launch_count() - launches0
+    ms, cnt, units = collect_profile(lib)
+    clocks = sampler.stop()
+    value = nvox * args.steps / t_step / 1e9
+
+    e2e = None
+    nbytes = int(nvox) * 2
+    if not args.skip_e2e:
+        import psutil
+        if nbytes * 1.5 < psutil.virtual_memory().available:
+            host = torch.empty(vol.shape, dtype=torch.int16).pin_memory()
+            host.copy_(vol)
+            torch.cuda.synchronize()
+            host_np = host.numpy().view(np.uint16)
+            b = run(host_np, "e2e")
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                b = run(host_np, "e2e")
+            torch.cuda.synchronize()
+            t_e2e = time.perf_counter() - t0
+            nb = 0 if b is None else int(b.shape[0])
+            e2e = {"value": nvox * args.steps / t_e2e / 1e9, "unit": UNIT,
+                   "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nb * b.shape[1] * 8
+                   if nb else 0,
+                   "table_equals_resident": bool(b is not None and final is not None
+                                                 and np.array_equal(b, final))}
+            del host, host_np
+
+    roof = roofline_block(ms, cnt, units)
+    cpu = None
+    if not args.skip_cpu:
+        if args.config == 1:
+            roi = vol.cpu().numpy().view(np.uint16)
+            t0 = time.perf_counter()
+            tab = mm.detect_blobs(roi, mm.Profile(), res)
+            dt = time.perf_counter() - t0
+            cpu = {"value": roi.size / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"the whole timed ROI, oracle detect_blobs in one process (the "
+                             f"reference's detect_blobs is single-process), {dt:.1f} s, "
+                             f"{0 if tab is None else len(tab)} blobs"}
+        else:
+            sshape = cpu_sample_shape(cores, shape)
+            if n_chl > 1:
+                sshape = (max(8, sshape[0] // (2 * n_chl)),) + sshape[1:]   # wide ladders cost more
+            tot_t, tot_v, notes = 0.0, 0.0, []
+            for c in chls:
+                sub = vol[:sshape[0], :sshape[1], :sshape[2]]
+                sub = (sub[..., c] if n_chl > 1 else sub).contiguous().cpu().numpy().view(np.uint16)
+                gv, dt, nb, nchunks = run_cpu_baseline(sub, near_maxs[c], cores,
+                                                       mm.Profile(**cfg["mods"][c]), res)
+                tot_t += dt
+                tot_v += sub.size
+                notes.append(f"channel {c}: {nchunks} chunks, {dt:.1f} s, {nb} blobs")
+            cpu = {"value": tot_v / tot_t / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"first {sshape[0]} planes x {sshape[1]} x {sshape[2]} of the timed "
+                             f"volume, the reference's own chunking, fork pool of {cores} "
+                             f"processes; " + "; ".join(notes)}
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t_step / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": cfg["what"].format(shape="x".join(str(v) for v in shape)),
+                   "l2": "inputs larger than L2" if nvox > 1e8 else
+                         "25 MB input: L2 flushed by the 51 MB float volumes each scale writes",
+                   "blobs_per_step": 0 if final is None else int(len(final)), "parity": parity},
+        "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+        "clocks": clocks,
+    }
+    print(json.dumps(out))
+
+
 # ----------------------------------------------------------------------------
 
 def main():
@@ -282,7 +544,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3])
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5])
     ap.add_argument("--mode", default="chunks", choices=["chunks", "seamless"])
     ap.add_argument("--shape", type=str, default=None,
                     help="z,y,x override: per GPU for config 2, the whole volume for config 3")
@@ -296,11 +558,20 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    shape = tuple(int(v) for v in args.shape.split(",")) if args.shape else SHAPES[args.config]
+    shape = tuple(int(v) for v in args.shape.split(",")) if args.shape else (
+        SHAPES.get(args.config) or NAMED[args.config]["shape"])
     cores = os.cpu_count() or 1
 
     if args.impl == "reference":
         run_reference(args, rank, world, shape, cores)
+        return
+
+    if args.config in NAMED:
+        if world > 1:
+            if rank == 0:
+                raise SystemExit("configs 1, 4 and 5 are single-GPU workloads")
+            return
+        main_named(args, shape, cores)
         return
 
     import torch
@@ -435,10 +706,7 @@ def main():
     n_blobs = 0 if final is None else len(final)
     stage_times = None if res is None or not getattr(res, "times", None) else {
         k.value: round(float(v[0]), 4) for k, v in res.times.items()}
-    import ctypes as C
-    ms = (C.c_double * 10)(); cnt = (C.c_int64 * 10)(); units = (C.c_double * 10)()
-    lib.mmb_profile_collect(ms, cnt, units)
-    lib.mmb_profile_enable(0)
+    ms, cnt, units = collect_profile(lib)
     clocks = sampler.stop() if rank == 0 else None
 
     # a step ends with host-side table assembly, so the step time is the larger of
@@ -510,49 +778,7 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (y sweep: 8 B in + 8 B out per voxel) --
-    peaks, peak_src = peaks_json()
-    kinds = ["to_float", "preprocess", "log_x", "log_y", "log_z", "localmax", "prune_edges",
-             "prune_resolve", "compact", "seam_match"]
-    alg_bytes = {"preprocess": 6.0, "log_x": 12.0, "log_y": 16.0, "log_z": 12.0, "localmax": 4.0}
-    per_kind = {}
-    total_ms = sum(ms)
-    for i, k in enumerate(kinds):
-        if cnt[i]:
-            per_kind[k] = {"ms": ms[i], "launches": int(cnt[i]), "share": ms[i] / total_ms,
-                           "gbps": (alg_bytes[k] * units[i] / (ms[i] * 1e-3) / 1e9
-                                    if k in alg_bytes else None)}
-    dom = max((k for k in per_kind if k in alg_bytes), key=lambda k: per_kind[k]["ms"])
-    # DRAM traffic of the dominant kernel from the committed ncu capture (bytes per
-    # voxel measured on one 505^3 chunk), scaled to this run's average launch size
-    traffic, traffic_src = None, None
-    for name in ("r02_traffic.json", "r01_traffic_v10.json"):
-        tpath = os.path.join(ROOT, "profiles", name)
-        if not os.path.exists(tpath):
-            continue
-        with open(tpath) as f:
-            tj = json.load(f)
-        if dom in tj["kernels"]:
-            vox_per_launch = units[kinds.index(dom)] / per_kind[dom]["launches"]
-            traffic = tj["kernels"][dom]["dram_bytes_per_voxel"] * vox_per_launch
-            traffic_src = (f"dram__bytes_read.sum + dram__bytes_write.sum per voxel from "
-                           f"profiles/{name} x this run's voxels per launch")
-            break
-    roof = {"bound": "hbm", "kernel": dom, "achieved": per_kind[dom]["gbps"],
-            "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": per_kind[dom]["gbps"] / peaks["hbm_gbs"], "traffic": traffic,
-            "traffic_source": traffic_src,
-            "algorithmic_bytes_per_launch": alg_bytes[dom] * units[kinds.index(dom)]
-            / per_kind[dom]["launches"],
-            "peak_source": f"{peak_src} copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
-            "avg_launch_ms": per_kind[dom]["ms"] / per_kind[dom]["launches"],
-            "algorithmic_bytes_per_voxel": alg_bytes[dom],
-            "units": "true voxels (X, not the padded row pitch) of rank 0's launches",
-            "fp32_colimit": "the three sweeps execute (14 r + 7) fp32 FMAs per voxel per scale "
-                            "(r = 12..20) as packed FFMA2; at the 128 lane-FMA/clk/SM pipe peak "
-                            "that alone takes as long as moving the algorithmic bytes at the "
-                            "measured HBM peak (DESIGN.md section 4)",
-            "per_kernel": per_kind}
+    roof = roofline_block(ms, cnt, units)
 
     cpu = None
     if not args.skip_cpu:

@@ -22,6 +22,12 @@ extern "C" {
 int mmb_synth_nuclei(uint16_t* out, int Z, int Y, int X, int64_t z_off, int64_t y_off,
                      int64_t x_off, uint64_t seed, double density, void* stream);
 
+/* Developer check: while on, every kernel launch of the library is followed (on the legacy
+ * default stream) by a kernel that fills the shared memory of every SM with 0xFFFFFFFF.
+ * A kernel that reads shared memory it never wrote then changes its results - shared
+ * memory has no initcheck.  Single-stream runs only (tools/poison_check.py).            */
+int mmb_debug_smem_poison(int on);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,28 @@ int encode_tensor_map_f32(CUtensorMap* map, const float* base, int rank, const u
 
 static thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
+std::atomic<int> g_debug_poison{0};
+
+// one CTA per SM, 200 KB of dynamic shared memory each, filled with 0xFFFFFFFF (NaN as
+// float, -1 as int): a kernel that consumes shared memory it never wrote then computes
+// differently from a run whose shared memory still holds a predecessor's finite values
+__global__ void __launch_bounds__(1024) poison_smem_kernel(unsigned pattern, unsigned* sink) {
+  extern __shared__ unsigned poison_s[];
+  const int n = 200 * 1024 / 4;
+  for (int i = threadIdx.x; i < n; i += 1024) poison_s[i] = pattern;
+  __syncthreads();
+  if (pattern == 1u && poison_s[(threadIdx.x * 97) % n] != pattern) *sink = 1;   // keep the stores
+}
+
+void debug_poison_smem() {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(poison_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         200 * 1024);
+    configured = true;
+  }
+  poison_smem_kernel<<<num_sms(), 1024, 200 * 1024, 0>>>(0xFFFFFFFFu, nullptr);
+}
 
 int num_sms() {
   static int cached[64] = {0};
@@ -152,6 +174,7 @@ static inline int64_t align256(int64_t x) { return (x + 255) / 256 * 256; }
 using namespace mmb;
 
 extern "C" int mmb_version(void) { return MMB_VERSION; }
+extern "C" int mmb_debug_smem_poison(int on) { g_debug_poison.store(on != 0); return MMB_OK; }
 extern "C" const char* mmb_last_error(void) { return g_err; }
 extern "C" int64_t mmb_launch_count(void) { return g_launches.load(); }
 

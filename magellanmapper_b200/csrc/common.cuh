@@ -10,6 +10,10 @@ namespace mmb {
 
 void set_error(const char* fmt, ...);
 extern std::atomic<int64_t> g_launches;
+// developer check (mmb_debug_smem_poison, include/mmb200_tools.h): after every launch
+// fill the shared memory of every SM with NaN bit patterns on the legacy default stream
+extern std::atomic<int> g_debug_poison;
+void debug_poison_smem();
 
 #define MMB_CHECK_CUDA(expr)                                                   \
   do {                                                                         \
@@ -25,6 +29,7 @@ extern std::atomic<int64_t> g_launches;
   do {                                                                         \
     mmb::g_launches.fetch_add(1, std::memory_order_relaxed);                   \
     MMB_CHECK_CUDA(cudaGetLastError());                                        \
+    if (mmb::g_debug_poison.load(std::memory_order_relaxed)) mmb::debug_poison_smem(); \
   } while (0)
 
 #define MMB_REQUIRE(cond, msg)                                                 \

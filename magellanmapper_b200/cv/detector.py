@@ -372,6 +372,127 @@ def cands_to_blobs(cands: np.ndarray, sigmas: np.ndarray, shape_yx: Sequence[int
     return Blobs(table).format_blobs(chl)
 
 
+def _unmixing_of(settings, chl: int):
+    """``{channel to subtract: factor}`` for ``chl`` (detector.py:910-921), or {}."""
+    spec = getattr(settings, "spectral_unmixing", None)
+    if not spec:
+        return {}
+    out = {}
+    for spec_chl, spec_subtr in spec.items():
+        if spec_chl == chl:
+            out.update(spec_subtr)
+    return out
+
+
+def detection_shape(shape: Sequence[int], channels: Sequence[int]) -> Tuple[int, int, int]:
+    """Shape of the volume ``blob_log`` sees for an ROI of ``shape``: the isotropic shape
+    when the first channel's profile asks for it (detector.py:893-897)."""
+    from . import cv_nd
+    isotropic = config.get_roi_profile(channels[0])["isotropic"]
+    if isotropic is None:
+        return tuple(int(v) for v in shape[:3])
+    return cv_nd.isotropic_shape(shape, isotropic)
+
+
+def enqueue_detection(det, roi, channels: Sequence[int], multichannel: bool,
+                      denoise_max_shape: Optional[Sequence[int]] = None):
+    """Launch, without waiting, everything ``detect_blobs`` does to an ROI up to and
+    including ``blob_log``, one fused chunk launch per channel on ``det`` (a
+    ``gpu.ChunkDetector`` that fits ``detection_shape``).  With ``denoise_max_shape``
+    the channels are first preprocessed block by block as ``detect_sub_roi`` does
+    (stack_detect.py:122-150).  Returns ``[(channel, sigmas, ticket)]``.
+
+    The common case is ONE launch per channel reading the caller's array in place.
+    Profiles with ``isotropic`` (detector.py:893-897) or ``spectral_unmixing``
+    (:910-921) go through intermediate float volumes instead: preprocess ->
+    ``mmb_resize_linear`` -> ``mmb_unmix_subtract`` -> detection."""
+    from .. import gpu
+    from . import cv_nd
+    scale = calc_scaling_factor()[2]
+    isotropic = config.get_roi_profile(channels[0])["isotropic"]
+    unmix = {c: _unmixing_of(config.get_roi_profile(c), c) for c in channels}
+    if any(unmix.values()) and not multichannel:
+        raise IndexError("spectral unmixing needs a multichannel ROI")
+    block = tuple(int(v) for v in denoise_max_shape) if denoise_max_shape is not None \
+        else (1, 1, 1)
+    tickets = []
+    if isotropic is None and not any(unmix.values()):
+        for chl in channels:
+            settings = config.get_roi_profile(chl)
+            src = gpu.as_source(roi, chl if multichannel else None)
+            pre, in_scale = None, 1.0
+            f32 = src.dtype == gpu._lib.MMB_F32
+            if denoise_max_shape is not None:
+                pre = plot_3d.preproc_params(settings, chl)
+                f32 = False      # preprocessing yields float64 in the reference
+            else:
+                np_dtype = roi.dtype if isinstance(roi, np.ndarray) else None
+                in_scale = input_scale(np_dtype) if np_dtype is not None else {
+                    gpu._lib.MMB_U8: 1 / 255.0, gpu._lib.MMB_U16: 1 / 65535.0}.get(src.dtype, 1.0)
+            sigmas = sigma_ladder(settings, scale, f32)
+            if det.free_slots() == 0:
+                raise RuntimeError("no free output slot: finish a pending sub-ROI first")
+            tickets.append((chl, sigmas, det.enqueue(
+                src, sigmas, settings["detection_threshold"], settings["overlap"],
+                scale=in_scale, pre=pre, block_shape=block)))
+        return tickets
+
+    shape = tuple(int(v) for v in roi.shape[:3])
+    iso_shape = shape if isotropic is None else cv_nd.isotropic_shape(shape, isotropic)
+    edge = cv_nd.edge_mode_for(roi.shape)
+    cache = {}
+
+    def volume(c):
+        """(pitched float32 volume in detection shape, raw integer scale or None, f32)"""
+        if c not in cache:
+            src = gpu.as_source(roi, c if multichannel else None)
+            int_scale = {gpu._lib.MMB_U8: 1 / 255.0, gpu._lib.MMB_U16: 1 / 65535.0}.get(src.dtype)
+            f32 = src.dtype == gpu._lib.MMB_F32
+            if denoise_max_shape is not None:
+                vol = gpu.preprocess_blocks(
+                    src, block, plot_3d.preproc_params(config.get_roi_profile(c), c))
+                src, int_scale, f32 = gpu.volume_source(vol, shape), None, False
+                if isotropic is None:
+                    cache[c] = (vol, None, False)
+                    return cache[c]
+            if isotropic is not None:
+                vol = gpu.resize_linear(src, iso_shape, edge)
+            else:
+                vol = gpu.to_float(src, 1.0)
+            cache[c] = (vol, int_scale, f32)
+        return cache[c]
+
+    for chl in channels:
+        settings = config.get_roi_profile(chl)
+        vol, int_scale, f32 = volume(chl)
+        in_scale = int_scale if int_scale is not None else 1.0
+        if unmix[chl]:
+            vol = vol.clone()
+            for subt_chl, subt_fac in unmix[chl].items():
+                gpu.unmix_subtract(vol, volume(int(subt_chl))[0], iso_shape[2], subt_fac)
+            # np.subtract(..., factor * other) is float64: img_as_float leaves it as it is
+            in_scale, f32 = 1.0, False
+        sigmas = sigma_ladder(settings, scale, f32)
+        if det.free_slots() == 0:
+            raise RuntimeError("no free output slot: finish a pending sub-ROI first")
+        tickets.append((chl, sigmas, det.enqueue(
+            gpu.volume_source(vol, iso_shape), sigmas, settings["detection_threshold"],
+            settings["overlap"], scale=in_scale)))
+    return tickets
+
+
+def scale_back_isotropic(blobs: np.ndarray, channels: Sequence[int]) -> np.ndarray:
+    """Blobs detected on the isotropic ROI back onto the original grid: relative and
+    absolute coordinates times ``1 / isotropic_factor`` (detector.py:944-951)."""
+    from . import cv_nd
+    isotropic = config.get_roi_profile(channels[0])["isotropic"]
+    if isotropic is None or blobs is None:
+        return blobs
+    factor = 1 / cv_nd.calc_isotropic_factor(isotropic)
+    blobs = Blobs.multiply_blob_rel_coords(blobs, factor)
+    return Blobs.multiply_blob_abs_coords(blobs, factor)
+
+
 def detect_blobs(roi, channel: Optional[Sequence[int]],
                  exclude_border: Optional[Sequence[Sequence[int]]] = None
                  ) -> Optional[np.ndarray]:
@@ -390,31 +511,19 @@ def detect_blobs(roi, channel: Optional[Sequence[int]],
     from .. import gpu
     shape = tuple(roi.shape)
     multichannel, channels = plot_3d.setup_channels(roi, channel, 3)
-    if config.get_roi_profile(channels[0])["isotropic"] is not None:
-        raise NotImplementedError(
-            "the 'isotropic' resize (cv_nd.make_isotropic) is not accelerated yet")
-    scale = calc_scaling_factor()[2]
-    detector = gpu.ChunkDetector(shape[:3])
+    channels = list(channels)
+    det_shape = detection_shape(shape, channels)
+    detector = gpu.ChunkDetector(det_shape, n_slots=max(4, len(channels)))
     blobs_all = []
-    for chl in channels:
-        settings = config.get_roi_profile(chl)
-        if getattr(settings, "spectral_unmixing", None):
-            raise NotImplementedError("spectral unmixing is not accelerated yet")
-        src = gpu.as_source(roi, chl if multichannel else None)
-        sigmas = sigma_ladder(settings, scale, src.dtype == gpu._lib.MMB_F32)
-        np_dtype = roi.dtype if isinstance(roi, np.ndarray) else None
-        in_scale = input_scale(np_dtype) if np_dtype is not None else (
-            1.0 / 65535.0 if src.dtype == gpu._lib.MMB_U16 else
-            (1.0 / 255.0 if src.dtype == gpu._lib.MMB_U8 else 1.0))
-        cands, _ = detector.detect(src, sigmas, settings["detection_threshold"],
-                                   settings["overlap"], scale=in_scale)
+    for chl, sigmas, ticket in enqueue_detection(detector, roi, channels, multichannel):
+        cands, _ = detector.collect(ticket)
         if len(cands) < 1:
             _logger.debug("No blobs detected for channel %s", chl)
             continue
-        blobs_all.append(cands_to_blobs(cands, sigmas, shape[1:3], chl))
+        blobs_all.append(cands_to_blobs(cands, sigmas, det_shape[1:3], chl))
     if not blobs_all:
         return None
-    blobs_all = np.vstack(blobs_all)
+    blobs_all = scale_back_isotropic(np.vstack(blobs_all), channels)
     if exclude_border is not None:
         blobs_all = get_blobs_interior(blobs_all, shape, *exclude_border)
     return blobs_all

@@ -169,43 +169,26 @@ class StackDetector(object):
             raise NotImplementedError("intensity co-localisation is outside the accelerated path")
         shape = tuple(sub_roi.shape)
         multichannel, channels = plot_3d.setup_channels(sub_roi, channel, 3)
-        scale = detector.calc_scaling_factor()[2]
+        channels = list(channels)
         if det is None:
-            det = cls._workspace(shape[:3])
-        tickets = []
-        for chl in channels:
-            settings = config.get_roi_profile(chl)
-            if settings["isotropic"] is not None:
-                raise NotImplementedError("the 'isotropic' resize is not accelerated yet")
-            src = gpu.as_source(sub_roi, chl if multichannel else None)
-            pre = None
-            in_scale = 1.0
-            f32 = src.dtype == gpu._lib.MMB_F32
-            if denoise_max_shape is not None:
-                pre = plot_3d.preproc_params(settings, chl)
-                f32 = False      # preprocessing yields float64 in the reference
-            else:
-                in_scale = {gpu._lib.MMB_U8: 1 / 255.0, gpu._lib.MMB_U16: 1 / 65535.0}.get(
-                    src.dtype, 1.0)
-            sigmas = detector.sigma_ladder(settings, scale, f32)
-            if det.free_slots() == 0:
-                raise RuntimeError("no free output slot: finish a pending sub-ROI first")
-            ticket = det.enqueue(
-                src, sigmas, settings["detection_threshold"], settings["overlap"],
-                scale=in_scale, pre=pre,
-                block_shape=denoise_max_shape if denoise_max_shape is not None else (1, 1, 1))
-            tickets.append((chl, sigmas, ticket))
+            det = cls._workspace(detector.detection_shape(shape, channels))
+        tickets = detector.enqueue_detection(det, sub_roi, channels, multichannel,
+                                             denoise_max_shape)
         return (coord, offset, last_coord, exclude_border, shape, det, tickets)
 
     @classmethod
     def finish_sub_roi(cls, pending) -> Tuple[Sequence[int], Optional[np.ndarray]]:
         coord, offset, last_coord, exclude_border, shape, det, tickets = pending
         tables = []
+        chls = [t[0] for t in tickets]
+        det_shape = detector.detection_shape(shape, chls) if chls else shape
         for chl, sigmas, ticket in tickets:
             cands, _ = det.collect(ticket)
             if len(cands):
-                tables.append(detector.cands_to_blobs(cands, sigmas, shape[1:3], chl))
+                tables.append(detector.cands_to_blobs(cands, sigmas, det_shape[1:3], chl))
         segments = np.vstack(tables) if tables else None
+        if segments is not None:
+            segments = detector.scale_back_isotropic(segments, chls)
         if segments is not None and exclude_border is not None:
             exclude = np.array([exclude_border, exclude_border])
             exclude[0, np.equal(coord, 0)] = 0
@@ -396,8 +379,11 @@ class StackDetector(object):
         cls.denoise_max_shape, cls.exclude_border = denoise_max_shape, exclude_border
         cls.coloc, cls.channel = coloc, channel
         seg_rois = np.zeros(sub_roi_slices.shape, dtype=object)
-        # size the workspace once for the largest chunk
+        # size the workspace once for the largest chunk (in the shape blob_log sees: the
+        # isotropic one when the profile resizes)
         largest = [max(s[a].stop - s[a].start for s in sub_roi_slices.flat) for a in range(3)]
+        largest = list(detector.detection_shape(
+            largest, list(plot_3d.setup_channels(img, channel, 3)[1])))
         det = cls._workspace(tuple(largest))
         n_chl = len(plot_3d.setup_channels(img, channel, 3)[1])
         if n_chl > det.n_slots - 1:
@@ -592,7 +578,8 @@ def detect_blobs_blocks(filename_base: str, img5d: np_io.Image5d,
         _, channels = plot_3d.setup_channels(roi, channels, 3)
     settings = config.get_roi_profile(channels[0])
     blocks = setup_blocks(settings, roi.shape)
-    if blocks.exclude_border is None and DEVICE_TABLES and not coloc:
+    if (blocks.exclude_border is None and DEVICE_TABLES and not coloc
+            and settings["isotropic"] is None):
         # per-chunk tables stay in HBM; merged, seam-pruned there, one copy back
         from . import device_tables
         tables = StackDetector.detect_blobs_sub_rois_device(

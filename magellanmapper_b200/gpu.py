@@ -241,6 +241,37 @@ def preprocess_blocks(src: Source, block_shape: Sequence[int], params: MmbPrepro
     return out
 
 
+def volume_source(vol: torch.Tensor, shape: Sequence[int]) -> Source:
+    """A pitched float32 device volume (``new_volume``) as a detection input."""
+    Z, Y, X = (int(v) for v in shape)
+    pitch = int(vol.shape[2])
+    return Source(vol, vol.data_ptr(), _lib.MMB_F32, (Y * pitch, pitch, 1), (Z, Y, X))
+
+
+def resize_linear(src: Source, out_shape: Sequence[int], edge: bool = False) -> torch.Tensor:
+    """``skimage.transform.resize(..., preserve_range=True).astype(dtype)`` as
+    ``cv_nd.make_isotropic`` uses it (``mmb_resize_linear``): returns the pitched
+    float32 volume of ``out_shape``; integer inputs come back truncated to integers.
+    ``edge``: 'edge' instead of 'reflect' boundaries."""
+    lib = _lib.load()
+    Z, Y, X = src.shape
+    Zo, Yo, Xo = (int(v) for v in out_shape)
+    out = new_volume(Zo, Yo, Xo, src.tensor.device)
+    _lib.check(lib.mmb_resize_linear(
+        C.c_void_p(src.ptr), src.dtype, _lib._I64x3(*src.strides), Z, Y, X, _ptr(out), Zo, Yo, Xo,
+        out.shape[2], 1 if edge else 0, _stream()))
+    return out
+
+
+def unmix_subtract(target: torch.Tensor, other: torch.Tensor, X: int, factor: float) -> None:
+    """``target = max(target - factor * other, 0)`` in place on two pitched volumes."""
+    Z, Y, pitch = target.shape
+    if tuple(other.shape) != tuple(target.shape):
+        raise ValueError(f"volumes differ: {tuple(target.shape)} vs {tuple(other.shape)}")
+    _lib.check(_lib.load().mmb_unmix_subtract(_ptr(target), _ptr(other), Z, Y, int(X), pitch,
+                                              float(factor), _stream()))
+
+
 def log_pass(in0, in1, X: int, axis: int, mode: int, sigma: float, scale: float = 1.0):
     """One separable sweep (see ``mmb_log_pass``); returns (out0, out1|None)."""
     lib = _lib.load()

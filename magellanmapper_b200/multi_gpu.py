@@ -442,8 +442,9 @@ def detect_blobs_blocks_slabs(filename_base: str, slab, held: Sequence[Range],
     loans = loan_units(rows, z_bounds, y_bounds, x_bounds) if balance_units else []
     lent = {(k, j) for k, j, _, _ in loans}
     host_slab = isinstance(slab, np.ndarray)
-    streamed = (host_slab and slab.flags.c_contiguous and blocks.exclude_border is None
-                and stack_detect.DEVICE_TABLES)
+    device_route = (blocks.exclude_border is None and stack_detect.DEVICE_TABLES
+                    and settings["isotropic"] is None)
+    streamed = host_slab and slab.flags.c_contiguous and device_route
     prefix = suffix = None
     if streamed:
         # the slab stays on the host and is streamed strip by strip under the kernels;
@@ -471,7 +472,7 @@ def detect_blobs_blocks_slabs(filename_base: str, slab, held: Sequence[Range],
     for c in np.ndindex(*grid):
         if local_slices[c] is None:
             local_slices[c] = (slice(0, 0), slice(0, 0), slice(0, 0))
-    if blocks.exclude_border is None and stack_detect.DEVICE_TABLES:
+    if device_route:
         # device-resident tables: the gather moves CUDA tensors over NVLink and rank 0
         # prunes the seams on its GPU
         from .cv import device_tables

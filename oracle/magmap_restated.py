@@ -48,6 +48,9 @@ class Profile:
     segment_size: float = 500
     denoise_size: Optional[float] = 25
     prune_tol_factor: Sequence[float] = (1, 1, 1)
+    isotropic: Optional[Sequence[float]] = None
+    #: ``{channel: {channel to subtract: factor}}`` (roi_prof.py:139-142)
+    spectral_unmixing: Optional[Dict[int, Dict[int, float]]] = None
 
 
 # --------------------------------------------------------------------------
@@ -206,24 +209,71 @@ def get_blobs_interior(blobs, shape, pad_start, pad_end):
     return blobs[m]
 
 
-def detect_blobs(roi: np.ndarray, prof: Profile, resolution: Sequence[float],
-                 channel: int = 0, exclude_border=None, full: bool = False):
-    """detector.py:874-957 for one channel, ``isotropic`` off, no spectral
-    unmixing.  Sigma range = factor x x-axis scaling (:903-927); radius =
-    sigma * sqrt(3) (:937)."""
+def calc_isotropic_factor(scale, resolution: Sequence[float]) -> np.ndarray:
+    """cv_nd.py:1040-1068."""
+    resize_factor = np.divide(resolution, np.amin(resolution))
+    return resize_factor * scale
+
+
+def make_isotropic(roi: np.ndarray, scale, resolution: Sequence[float]) -> np.ndarray:
+    """cv_nd.py:1071-1167: ``transform.resize`` to ``(shape[:3] * factor).astype(int)``
+    with ``preserve_range=True``, 'reflect' boundaries ('edge' when any axis is one voxel
+    thick), cast back to the ROI's dtype."""
+    factor = calc_isotropic_factor(scale, resolution)
+    iso = np.array(roi.shape)
+    iso[:3] = (iso[:3] * factor).astype(int)
+    mode = "edge" if np.any(np.array(roi.shape) == 1) else "reflect"
+    out = ski.transform_resize(roi, iso, mode=mode, preserve_range=True)
+    return out.astype(roi.dtype)
+
+
+def detect_blobs(roi: np.ndarray, prof, resolution: Sequence[float],
+                 channel=0, exclude_border=None, full: bool = False):
+    """detector.py:874-957.  ``prof`` is one ``Profile`` or one per channel of a
+    ``(z, y, x, c)`` ROI; ``channel`` an index or a list of them.  ``isotropic`` resize
+    with the FIRST channel's setting (:893-897), spectral unmixing per channel
+    (:910-921), sigma range = factor x x-axis scaling (:903-927), radius =
+    sigma * sqrt(3) (:937), coordinates scaled back and cast to int (:944-951)."""
+    shape = roi.shape
+    multichannel = roi.ndim > 3
+    channels = list(channel) if isinstance(channel, (list, tuple, range)) else [channel]
+    profs = list(prof) if isinstance(prof, (list, tuple)) else None
+    get = (lambda c: profs[c]) if profs is not None else (lambda c: prof)
+    isotropic = get(channels[0]).isotropic
+    if isotropic is not None:
+        roi = make_isotropic(roi, isotropic, resolution)
     scale = calc_scaling_factor(resolution)[2]
-    res = ski.blob_log(
-        roi, min_sigma=prof.min_sigma_factor * scale,
-        max_sigma=prof.max_sigma_factor * scale, num_sigma=prof.num_sigma,
-        threshold=prof.detection_threshold, overlap=prof.overlap, full=True)
-    if res.blobs.size < 1:
-        return (None, res) if full else None
-    b = res.blobs.copy()
-    b[:, 3] = b[:, 3] * math.sqrt(3)
-    out = format_blobs(b, channel)
+    tables, last = [], None
+    for chl in channels:
+        p = get(chl)
+        roi_detect = roi[..., chl] if multichannel else roi
+        if p.spectral_unmixing is not None:
+            for spec_chl, spec_subtr in p.spectral_unmixing.items():
+                if spec_chl != chl:
+                    continue
+                for subt_chl, subt_fac in spec_subtr.items():
+                    roi_detect = np.subtract(roi_detect, subt_fac * roi[..., subt_chl])
+                    roi_detect[roi_detect < 0] = 0
+        res = ski.blob_log(
+            roi_detect, min_sigma=p.min_sigma_factor * scale,
+            max_sigma=p.max_sigma_factor * scale, num_sigma=p.num_sigma,
+            threshold=p.detection_threshold, overlap=p.overlap, full=True)
+        last = res
+        if res.blobs.size < 1:
+            continue
+        b = res.blobs.copy()
+        b[:, 3] = b[:, 3] * math.sqrt(3)
+        tables.append(format_blobs(b, chl))
+    if not tables:
+        return (None, last) if full else None
+    out = np.vstack(tables)
+    if isotropic is not None:
+        f = 1 / calc_isotropic_factor(isotropic, resolution)
+        out[:, 0:3] = np.multiply(out[:, 0:3], f).astype(int)
+        out[:, 7:10] = np.multiply(out[:, 7:10], f).astype(int)
     if exclude_border is not None:
-        out = get_blobs_interior(out, roi.shape, *exclude_border)
-    return (out, res) if full else out
+        out = get_blobs_interior(out, shape, *exclude_border)
+    return (out, last) if full else out
 
 
 # --------------------------------------------------------------------------

@@ -239,6 +239,65 @@ def gen_stack_small(ns):
     np.savez_compressed(os.path.join(OUT, "stack_small.npz"), **out)
 
 
+def gen_iso_unmix(ns):
+    """detector.detect_blobs with the ``isotropic`` resize (up- and down-scaling, raw
+    uint16 and preprocessed float64 input), with spectral unmixing on a two-channel ROI,
+    and detect_blobs_blocks with ``isotropic`` + ``exclude_border`` (the lightsheet
+    profile's combination) - all through the UNMODIFIED reference."""
+    out = {}
+    vol, _ = synth.make_volume((20, 56, 48), seed=61, density=1 / 1500.0)
+    near_max = synth.near_max_of(vol)
+    out["vol"] = vol
+    out["near_max"] = np.array(near_max)
+    # up-scaling z: 3 um planes, 1 um pixels, 0.96 of isotropic -> 57 planes
+    ref_shim.set_profile(ns, (3, 1, 1), near_max=near_max, isotropic=(0.96, 1, 1))
+    out["iso_up_resized"] = ns.cv_nd.make_isotropic(vol, (0.96, 1, 1))
+    out["iso_up_raw"] = ns.detector.detect_blobs(vol, [0])
+    pre = ns.plot_3d.denoise_roi(ns.plot_3d.saturate_roi(vol))
+    out["pre"] = pre.astype(np.float64)
+    out["iso_up_pre_resized"] = ns.cv_nd.make_isotropic(pre, (0.96, 1, 1))
+    out["iso_up_pre"] = ns.detector.detect_blobs(pre, [0], np.array([[1, 2, 0], [0, 3, 2]]))
+    # shrinking y and x (anti-aliasing Gaussian), growing z
+    ref_shim.set_profile(ns, (1, 1, 1), near_max=near_max, isotropic=(1.5, 0.6, 0.75))
+    out["iso_mixed_resized"] = ns.cv_nd.make_isotropic(vol, (1.5, 0.6, 0.75))
+    out["iso_mixed_pre_resized"] = ns.cv_nd.make_isotropic(pre, (1.5, 0.6, 0.75))
+    out["iso_mixed_pre"] = ns.detector.detect_blobs(pre, [0])
+    # spectral unmixing: channel 0 minus 0.4 x channel 1, channel 1 as it is
+    v1, _ = synth.make_volume(vol.shape, seed=62, density=1 / 1500.0)
+    two = np.stack([vol, v1], axis=-1)
+    out["two"] = two
+    p0 = ref_shim.set_profile(ns, (1, 1, 1), near_max=near_max)
+    p1 = ns.roi_prof.ROIProfile()
+    p1.add_profiles("/root/reference/profiles/roi_blobs.yaml")
+    p0.spectral_unmixing = {0: {1: 0.4}}
+    ns.config.roi_profiles = [p0, p1]
+    ns.config.near_max = [near_max, synth.near_max_of(v1)]
+    out["near_max1"] = np.array(ns.config.near_max[1])
+    pre2 = ns.plot_3d.denoise_roi(ns.plot_3d.saturate_roi(two))
+    out["pre2"] = pre2.astype(np.float64)
+    out["unmix_pre"] = ns.detector.detect_blobs(pre2, None)
+    # stack: isotropic + exclude_border, anisotropic chunk geometry
+    shape = (24, 100, 90)
+    svol, _ = synth.make_volume(shape, seed=63, density=1 / 2000.0)
+    snm = synth.near_max_of(svol)
+    out["svol"] = svol
+    out["snm"] = np.array(snm)
+    ref_shim.set_profile(ns, (2.5, 1, 1), near_max=snm, isotropic=(0.96, 1, 1),
+                         segment_size=40, exclude_border=(1, 0, 0))
+    img5d = ns.np_io.Image5d(svol[None])
+    with tempfile.TemporaryDirectory() as td:
+        ns.config.filename = os.path.join(td, "synth")
+        cwd = os.getcwd()
+        os.chdir(td)
+        try:
+            _, _, blobs = ns.stack_detect.detect_blobs_blocks(
+                ns.config.filename, img5d, None, None, [0], False, False, True)
+        finally:
+            os.chdir(cwd)
+    out["stack_iso_blobs"] = blobs.blobs
+    np.savez_compressed(os.path.join(OUT, "iso_unmix.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_shim.load_reference()
@@ -250,6 +309,7 @@ def main():
     gen_preprocess(ns)
     gen_detect_small(ns)
     gen_stack_small(ns)
+    gen_iso_unmix(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

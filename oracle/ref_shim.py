@@ -54,7 +54,7 @@ def load_reference():
         return _loaded
     sys.meta_path.append(_MissingFinder())
     sys.path.insert(0, REFERENCE_ROOT)
-    from magmap.cv import chunking, detector, stack_detect      # noqa
+    from magmap.cv import chunking, cv_nd, detector, stack_detect      # noqa
     from magmap.plot import plot_3d                              # noqa
     from magmap.settings import config, roi_prof                 # noqa
     from magmap.io import np_io                                  # noqa
@@ -67,10 +67,14 @@ def load_reference():
     plot_3d.morphology.octahedron = lambda r: ski.octahedron1()
     plot_3d.morphology.erosion = lambda img, fp: ski.erosion_octahedron1(img)
 
+    # cv_nd.py:1147 - transform.resize (make_isotropic)
+    cv_nd.transform.resize = ski.transform_resize
+
     class NS:
         pass
     ns = NS()
     ns.chunking, ns.detector, ns.stack_detect = chunking, detector, stack_detect
+    ns.cv_nd = cv_nd
     ns.plot_3d, ns.config, ns.roi_prof, ns.np_io = plot_3d, config, roi_prof, np_io
     _loaded = ns
     return ns

@@ -291,3 +291,56 @@ def erosion_octahedron1(image: np.ndarray) -> np.ndarray:
     a radius-1 neighbour outside the array mirrors onto the voxel itself (the
     older max-value padding gives the same minimum)."""
     return ndi.grey_erosion(image, footprint=octahedron1(), mode="reflect")
+
+
+def transform_resize(image: np.ndarray, output_shape: Sequence[int], order=None,
+                     mode: str = "reflect", cval: float = 0, clip: bool = True,
+                     preserve_range: bool = False, anti_aliasing=None,
+                     anti_aliasing_sigma=None) -> np.ndarray:
+    """``skimage.transform.resize`` (``skimage/transform/_warps.py``, 0.19 - 0.25) for the
+    n-D ``scipy.ndimage.zoom`` route, as ``magmap.cv.cv_nd.rescale_resize`` calls it:
+
+    * ``order=None`` -> 0 for bool images, 1 otherwise; float conversion with
+      ``preserve_range`` keeps float32 / float64 and widens everything else to float64;
+    * ``anti_aliasing=None`` -> on when any axis shrinks (never for bool, nor for
+      integer images with ``order == 0``): ``ndi.gaussian_filter`` with ``sigma =
+      max(0, (in / out - 1) / 2)`` per axis in the translated boundary mode;
+    * ``np.pad`` mode names translate to ``scipy.ndimage`` ones: 'reflect' -> 'mirror',
+      'symmetric' -> 'reflect', 'edge' -> 'nearest';
+    * ``ndi.zoom(..., order, mode, cval, grid_mode=True)`` with zoom factors ``out / in``;
+    * ``clip`` -> ``np.clip`` to the input's value range.
+    """
+    image = np.asarray(image)
+    output_shape = tuple(int(v) for v in output_shape)
+    if len(output_shape) != image.ndim:
+        raise ValueError("output_shape must have one entry per image axis")
+    input_shape = image.shape
+    input_type = image.dtype
+    if input_type == np.float16:
+        image = image.astype(np.float32)
+    if order is None:
+        order = 0 if input_type == bool else 1
+    if anti_aliasing is None:
+        anti_aliasing = (input_type != bool
+                         and not (np.issubdtype(input_type, np.integer) and order == 0)
+                         and any(o < i for o, i in zip(output_shape, input_shape)))
+    factors = np.divide(input_shape, output_shape)
+    if order > 0:
+        if preserve_range:
+            if image.dtype.char not in "df":
+                image = image.astype(float)
+        else:
+            image = img_as_float(image)
+    ndi_mode = {"constant": "constant", "edge": "nearest", "symmetric": "reflect",
+                "reflect": "mirror", "wrap": "wrap"}[mode]
+    filtered = image
+    if anti_aliasing:
+        if anti_aliasing_sigma is None:
+            anti_aliasing_sigma = np.maximum(0, (factors - 1) / 2)
+        filtered = ndi.gaussian_filter(image, anti_aliasing_sigma, cval=cval, mode=ndi_mode)
+    zoom_factors = [1 / f for f in factors]
+    out = ndi.zoom(filtered, zoom_factors, order=order, mode=ndi_mode, cval=cval,
+                   grid_mode=True)
+    if clip and out.size:
+        np.clip(out, np.min(image), np.max(image), out=out)
+    return out

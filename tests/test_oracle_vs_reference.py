@@ -155,3 +155,29 @@ def test_near_bounds_oracle_vs_reference(golden_dir):
         np.testing.assert_array_equal(np.ravel(near_maxs), np.ravel(g[f"{name}_near_maxs"]))
         lo, hi = mm.calc_intensity_bounds(vol, channel_axis=3 if multichannel else None)
         np.testing.assert_array_equal(np.array([lo, hi]), g[f"{name}_whole"])
+
+
+def test_isotropic_and_unmixing(golden_dir):
+    """``make_isotropic`` (up-scaling, and shrinking with the anti-aliasing Gaussian),
+    ``detect_blobs`` with ``isotropic`` and with spectral unmixing, and the stack driver
+    with ``isotropic`` + ``exclude_border``, against the unmodified reference."""
+    g = _load(golden_dir, "iso_unmix.npz")
+    vol, pre, nm = g["vol"], g["pre"], float(g["near_max"])
+    np.testing.assert_array_equal(mm.make_isotropic(vol, (0.96, 1, 1), (3, 1, 1)),
+                                  g["iso_up_resized"])
+    np.testing.assert_array_equal(mm.make_isotropic(pre, (0.96, 1, 1), (3, 1, 1)),
+                                  g["iso_up_pre_resized"])
+    np.testing.assert_array_equal(mm.make_isotropic(vol, (1.5, 0.6, 0.75), (1, 1, 1)),
+                                  g["iso_mixed_resized"])
+    up = mm.Profile(isotropic=(0.96, 1, 1))
+    np.testing.assert_array_equal(mm.detect_blobs(vol, up, (3, 1, 1)), g["iso_up_raw"])
+    np.testing.assert_array_equal(
+        mm.detect_blobs(pre, up, (3, 1, 1), 0, np.array([[1, 2, 0], [0, 3, 2]])), g["iso_up_pre"])
+    mixed = mm.Profile(isotropic=(1.5, 0.6, 0.75))
+    np.testing.assert_array_equal(mm.detect_blobs(pre, mixed, (1, 1, 1)), g["iso_mixed_pre"])
+    p0 = mm.Profile(spectral_unmixing={0: {1: 0.4}})
+    np.testing.assert_array_equal(
+        mm.detect_blobs(g["pre2"], [p0, mm.Profile()], (1, 1, 1), [0, 1]), g["unmix_pre"])
+    prof = mm.Profile(isotropic=(0.96, 1, 1), segment_size=40, exclude_border=(1, 0, 0))
+    final = mm.detect_blobs_blocks(g["svol"], prof, (2.5, 1, 1), float(g["snm"]))
+    np.testing.assert_array_equal(final, g["stack_iso_blobs"])

@@ -17,7 +17,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from magellanmapper_b200 import gpu, _lib            # noqa: E402
+from magellanmapper_b200 import gpu, _lib, synth     # noqa: E402
 import bench                                           # noqa: E402
 
 
@@ -57,7 +57,7 @@ def main():
     sm_clock = 1.965e9
     fma_peak = 148 * 128 * sm_clock            # FFMA lanes / s
 
-    vol = bench.make_device_volume((Z, Y, X), 1, dev)
+    vol = synth.device_volume((Z, Y, X), 1, device=dev)
     nm = bench.near_max_device(vol)
     src = gpu.as_source(vol)
     from magellanmapper_b200._lib import MmbPreprocParams

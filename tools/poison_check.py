@@ -61,3 +61,17 @@ for pat in (0xFF, 0x00, 0x7F, 0xFF):
         b = {tuple(r) for r in v[:, :4]}
         print("  only in ref:", sorted(a - b)[:6])
         print("  only in poisoned:", sorted(b - a)[:6])
+
+# shared memory: every launch followed by a NaN fill of the shared memory of every SM
+gpu.ChunkDetector.enqueue = orig
+from magellanmapper_b200 import _lib
+_lib.load().mmb_debug_smem_poison(1)
+v = run()
+_lib.load().mmb_debug_smem_poison(0)
+d = int(np.count_nonzero(np.any(v != ref, axis=1))) if v.shape == ref.shape else -1
+print(f"shared-memory poison: rows {v.shape[0]} differing {d}", flush=True)
+if d:
+    a = {tuple(r) for r in ref[:, :4]}
+    b = {tuple(r) for r in v[:, :4]}
+    print("  only in ref:", sorted(a - b)[:6])
+    print("  only in poisoned:", sorted(b - a)[:6])

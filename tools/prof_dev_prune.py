@@ -2,12 +2,13 @@ import sys, time, os
 sys.path.insert(0, "/root/repo")
 import numpy as np, torch
 import bench
+from magellanmapper_b200 import synth
 from magellanmapper_b200 import gpu
 from magellanmapper_b200.cv import stack_detect, device_tables
 from magellanmapper_b200.io import np_io
 from magellanmapper_b200.settings import config
 dev = torch.device("cuda", 0)
-vol = bench.make_device_volume((512, 2048, 2048), 1, dev)
+vol = synth.device_volume((512, 2048, 2048), 1, device=dev)
 nm = bench.near_max_device(vol)
 bench.setup_config(nm, "/tmp/x")
 settings = config.get_roi_profile(0)

@@ -2,10 +2,11 @@ import sys, os, cProfile, pstats, time, tempfile
 sys.path.insert(0, os.getcwd())
 import torch, numpy as np
 import bench
+from magellanmapper_b200 import synth
 from magellanmapper_b200.cv import stack_detect
 from magellanmapper_b200.io import np_io
 dev = torch.device("cuda", 0)
-vol = bench.make_device_volume(bench.SHAPE_FULL, 1, dev)
+vol = synth.device_volume(bench.SHAPES[2], 1, device=dev)
 nm = bench.near_max_device(vol)
 tmp = tempfile.mkdtemp(); os.chdir(tmp)
 bench.setup_config(nm, os.path.join(tmp, "x"))

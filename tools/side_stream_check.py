@@ -6,6 +6,7 @@ import sys, os, tempfile
 sys.path.insert(0, "/root/repo")
 import numpy as np, torch
 import bench
+from magellanmapper_b200 import synth
 from magellanmapper_b200.cv import stack_detect
 from magellanmapper_b200.io import np_io
 from magellanmapper_b200.settings import config
@@ -18,7 +19,7 @@ config.roi_profile["segment_size"] = 50
 _, _, b = stack_detect.detect_blobs_blocks(tmp + "/g", np_io.Image5d(g["vol"][None]), None, None, [0], False, False, True)
 print("golden equal:", np.array_equal(b.blobs, g["plain_blobs"]))
 stack_detect.StackDetector.release_workspace()
-vol = bench.make_device_volume((512, 2048, 2048), 1, dev)
+vol = synth.device_volume((512, 2048, 2048), 1, device=dev)
 nm = bench.near_max_device(vol)
 bench.setup_config(nm, tmp + "/c2")
 def run(img):
