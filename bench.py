@@ -151,13 +151,16 @@ def peaks_json():
 
 
 KINDS = ["to_float", "preprocess", "log_x", "log_y", "log_z", "localmax", "prune_edges",
-         "prune_resolve", "compact", "seam_match"]
-ALG_BYTES = {"preprocess": 6.0, "log_x": 12.0, "log_y": 16.0, "log_z": 12.0, "localmax": 4.0}
+         "prune_resolve", "compact", "seam_match", "log_xy"]
+#: algorithmic bytes per voxel and launch: float32 volumes
+#: read + written, uint16 input for the preprocessing
+ALG_BYTES = {"preprocess": 6.0, "log_x": 12.0, "log_y": 16.0, "log_z": 12.0, "localmax": 4.0,
+             "log_xy": 12.0}
 
 
 def collect_profile(lib):
     import ctypes as C
-    ms = (C.c_double * 10)(); cnt = (C.c_int64 * 10)(); units = (C.c_double * 10)()
+    ms = (C.c_double * 16)(); cnt = (C.c_int64 * 16)(); units = (C.c_double * 16)()
     lib.mmb_profile_collect(ms, cnt, units)
     lib.mmb_profile_enable(0)
     return ms, cnt, units

@@ -297,8 +297,9 @@ int64_t mmb_launch_count(void);
  * events and sums, per kernel kind, elapsed milliseconds, launch count and work
  * units (voxels; candidates for the prune kernels; pairs for the seam match).
  * Kinds: 0 to_float, 1 preprocess, 2 log_x, 3 log_y, 4 log_z, 5 localmax,
- * 6 prune_edges, 7 prune_resolve, 8 compact, 9 seam_match.                    */
-#define MMB_PROF_NKINDS 10
+ * 6 prune_edges, 7 prune_resolve, 8 compact, 9 seam_match, 10 log_xy (the fused
+ * x -> y sweep; log_x / log_y then only count the volumes it does not serve).     */
+#define MMB_PROF_NKINDS 11
 int mmb_profile_enable(int on);
 int mmb_profile_collect(double ms[MMB_PROF_NKINDS], int64_t launches[MMB_PROF_NKINDS],
                         double units[MMB_PROF_NKINDS]);

@@ -104,7 +104,7 @@ static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // output arrays.
 enum ProfKind {
   PROF_TO_FLOAT = 0, PROF_PREPROCESS, PROF_LOG_X, PROF_LOG_Y, PROF_LOG_Z, PROF_LOCALMAX,
-  PROF_PRUNE_EDGES, PROF_PRUNE_RESOLVE, PROF_COMPACT, PROF_SEAM, PROF_NKINDS
+  PROF_PRUNE_EDGES, PROF_PRUNE_RESOLVE, PROF_COMPACT, PROF_SEAM, PROF_LOG_XY, PROF_NKINDS
 };
 bool prof_enabled();
 void prof_begin(int kind, double units, cudaStream_t st);

@@ -1,5 +1,6 @@
 // LoG scale entry points: weights, sweep dispatch, generic large-radius fallback.
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 #include "log_kernels.cuh"
 
@@ -141,9 +142,22 @@ int log_scale_impl(const float* in, float* out, float* work, int Z, int Y, int X
   float* B = work + vol;
   float* C = work + 2 * vol;
   float* D = work + 3 * vol;
-  int rc = log_pass(in, nullptr, A, B, Z, Y, X, pitch, 2, MODE_FIRST, sigma, 1.0, st);
-  if (rc) return rc;
-  rc = log_pass(A, B, C, D, Z, Y, X, pitch, 1, MODE_MID, sigma, 1.0, st);
+  int rc = MMB_ERR_UNSUPPORTED;
+  static const bool no_fused = getenv("MMB_NO_FUSED_XY") != nullptr;   // developer A/B switch
+  if (!no_fused) {
+    LogWeights w;
+    const int r = make_log_weights(sigma, &w);
+    if (r >= 0 && Y <= 65535) {
+      prof_set_unit_scale((double)X / (double)pitch);
+      rc = launch_xy_fused(r, in, C, D, Z, Y, X, pitch, w, st);
+      prof_set_unit_scale(1.0);
+    }
+  }
+  if (rc == MMB_ERR_UNSUPPORTED) {
+    rc = log_pass(in, nullptr, A, B, Z, Y, X, pitch, 2, MODE_FIRST, sigma, 1.0, st);
+    if (rc) return rc;
+    rc = log_pass(A, B, C, D, Z, Y, X, pitch, 1, MODE_MID, sigma, 1.0, st);
+  }
   if (rc) return rc;
   return log_pass(C, D, out, nullptr, Z, Y, X, pitch, 0, MODE_LAST, sigma, -(sigma * sigma), st);
 }

@@ -502,6 +502,9 @@ int launch_strided_m2(int r, const float*, const float*, float*, float*, int, in
                       int64_t, const LogWeights&, float, cudaStream_t);
 int launch_x_first(int r, const float* in, float* outA, float* outB, int64_t nrows, int X,
                    int64_t pitch, const LogWeights& w, cudaStream_t st);
+// fused x -> y sweep (log_xy.cu); MMB_ERR_UNSUPPORTED = take the two separate sweeps
+int launch_xy_fused(int r, const float* in, float* outC, float* outD, int Z, int Y, int X,
+                    int64_t pitch, const LogWeights& w, cudaStream_t st);
 
 // Radius buckets with a compiled kernel; a request is served by the smallest
 // bucket >= r (taps beyond r carry zero weight).
