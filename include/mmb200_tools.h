@@ -22,6 +22,12 @@ extern "C" {
 int mmb_synth_nuclei(uint16_t* out, int Z, int Y, int X, int64_t z_off, int64_t y_off,
                      int64_t x_off, uint64_t seed, double density, void* stream);
 
+/* The fused x -> y sweep of mmb_log_scale on its own (csrc/log_xy.cu): C = g_y*(g_x*in),
+ * D = h_y*(g_x*in) + g_y*(h_x*in).  MMB_ERR_UNSUPPORTED for the shapes and radii that
+ * mmb_log_scale serves with the two separate sweeps (radius > 20, Y < 64, X < 32).     */
+int mmb_log_xy_fused(const float* in, float* outC, float* outD, int Z, int Y, int X,
+                     int64_t pitch, double sigma, void* stream);
+
 /* Developer check: while on, every kernel launch of the library is followed (on the legacy
  * default stream) by a kernel that fills the shared memory of every SM with 0xFFFFFFFF.
  * A kernel that reads shared memory it never wrote then changes its results - shared

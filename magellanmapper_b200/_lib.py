@@ -115,6 +115,8 @@ SIGNATURES = {
 #: bench / test utilities of include/mmb200_tools.h (not the reference-facing boundary)
 TOOLS_SIGNATURES = {
     "mmb_debug_smem_poison": (C.c_int, [C.c_int]),
+    "mmb_log_xy_fused": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int64,
+                                   C.c_double, _vp]),
     "mmb_synth_nuclei": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64,
                                    C.c_int64, C.c_uint64, C.c_double, _vp]),
 }

@@ -183,6 +183,24 @@ extern "C" int mmb_log_pass(const float* in0, const float* in1, float* out0, flo
                   (cudaStream_t)stream);
 }
 
+extern "C" int mmb_log_xy_fused(const float* in, float* outC, float* outD, int Z, int Y, int X,
+                                int64_t pitch, double sigma, void* stream) {
+  MMB_REQUIRE(in && outC && outD, "null buffer");
+  MMB_REQUIRE(Z > 0 && Y > 0 && X > 0 && pitch >= X, "bad shape");
+  MMB_REQUIRE(sigma > 0, "sigma must be positive");
+  LogWeights w;
+  const int r = make_log_weights(sigma, &w);
+  if (r < 0 || Y > 65535) {
+    set_error("radius of sigma %g is outside the fused sweep", sigma);
+    return MMB_ERR_UNSUPPORTED;
+  }
+  prof_set_unit_scale((double)X / (double)pitch);
+  const int rc = launch_xy_fused(r, in, outC, outD, Z, Y, X, pitch, w, (cudaStream_t)stream);
+  prof_set_unit_scale(1.0);
+  if (rc == MMB_ERR_UNSUPPORTED) set_error("shape or radius outside the fused sweep");
+  return rc;
+}
+
 extern "C" int mmb_log_scale(const float* in, float* out, void* work, int Z, int Y, int X,
                              int64_t pitch, double sigma, void* stream) {
   MMB_REQUIRE(in && out && work, "null buffer");

@@ -58,8 +58,9 @@ conv_x_tma_kernel(const __grid_constant__ CUtensorMap tm_in,
   using G = XGeom<R>;
   extern __shared__ unsigned char smem_raw[];
   // swizzled boxes need 1024-byte alignment
-  unsigned char* base = reinterpret_cast<unsigned char*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // aligned up on the 32-bit SHARED address, as an offset from smem_raw: a round trip through
+  // uintptr_t would make every later access a generic LD / ST with 64-bit address arithmetic
+  unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* s_in = base;
   unsigned char* s_a = base + kXStages * G::STAGE_BYTES;
   unsigned char* s_b = s_a + 4 * kBoxBytes;
@@ -253,8 +254,9 @@ conv_x_ws_kernel(const __grid_constant__ CUtensorMap tm_in,
                  float* __restrict__ outB, int64_t pitch) {
   using G = WsGeom<R>;
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* base = reinterpret_cast<unsigned char*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // aligned up on the 32-bit SHARED address, as an offset from smem_raw: a round trip through
+  // uintptr_t would make every later access a generic LD / ST with 64-bit address arithmetic
+  unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* s_in = base;
   unsigned char* s_out = base + kWsIn * G::STAGE_BYTES;
 #ifdef MMB_WS_DIRECT

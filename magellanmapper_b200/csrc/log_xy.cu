@@ -33,9 +33,17 @@
 
 namespace mmb {
 
-constexpr int kFCols = 128;            // x columns per CTA
+// x columns per CTA: 64 columns = 128 threads and ~45 KB of shared memory, i.e. four CTAs per
+// SM whose barriers are independent of one another; with 128 columns (two CTAs of 256
+// threads) the FP32 pipe idles at every phase change (measured: 0.84 vs 0.xx ms at r = 16)
+#ifndef MMB_XY_COLS
+#define MMB_XY_COLS 64
+#endif
+constexpr int kFCols = MMB_XY_COLS;
 constexpr int kFRows = 32;             // rows per step (= lanes of the x phase)
-constexpr int kFThreads = 256;
+constexpr int kFThreads = 2 * kFCols;  // x phase: 32 lanes x kFCols/16 segments; y phase: kFCols/2 pairs x 4 groups
+constexpr int kFPairs = kFCols / 2;
+constexpr int kFChunks = kFCols / 4;   // 16-byte chunks per ring row
 constexpr int kFBox = 32 * 32 * 4;     // bytes of one TMA box
 constexpr int kFRowB = kFCols * 4;     // ring row pitch in bytes
 
@@ -97,17 +105,18 @@ __device__ __forceinline__ void xy_scatter(const unsigned char* const (&bp)[NBLK
   }
 }
 
-// grid = (ceil(pitch / 128), segments of the y axis, Z); block = 256; 2 CTAs per SM
+// grid = (ceil(pitch / kFCols), segments of the y axis, Z); block = 2 kFCols; 512 threads per SM
 template <int R>
-__global__ void __launch_bounds__(kFThreads, 2)
+__global__ void __launch_bounds__(kFThreads, 512 / kFThreads)
 conv_xy_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ in,
                      float* __restrict__ outC, float* __restrict__ outD, int Y, int X,
                      int64_t pitch, int seg_len, const __grid_constant__ LogWeights w) {
   using G = FGeom<R>;
   constexpr int RP = G::RP, RR = G::RR, R4 = G::R4;
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* base = reinterpret_cast<unsigned char*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // aligned up on the 32-bit SHARED address, as an offset from smem_raw: a round trip through
+  // uintptr_t would make every later access a generic LD / ST with 64-bit address arithmetic
+  unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* s_in = base;                           // one TMA stage (1024-aligned)
   unsigned char* ringA = base + G::STAGE;
   uint64_t* bar = reinterpret_cast<uint64_t*>(ringA + 2 * G::RINGB);
@@ -143,12 +152,12 @@ conv_xy_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __r
   // 'reflect' rows: ring row q (outside [0, Y)) := ring row reflect(q), rows [q_lo, q_hi)
   auto mirror_rows = [&](int q_lo, int q_hi) {
     const int nq = q_hi - q_lo;
-    for (int i = tid; i < nq * 64; i += kFThreads) {
-      const int q = q_lo + (i >> 6), c = i & 63;        // 32 chunks of A, then 32 of B
+    for (int i = tid; i < nq * 2 * kFChunks; i += kFThreads) {
+      const int q = q_lo + i / (2 * kFChunks), c = i % (2 * kFChunks);   // chunks of A, then of B
       const int src = reflect_index(q, Y);
       int sd = (q - row_first) % RR, ss = (src - row_first) % RR;
-      const uint32_t arr = (c >> 5) * G::RINGB;
-      const int ch = c & 31;
+      const uint32_t arr = (c / kFChunks) * G::RINGB;
+      const int ch = c % kFChunks;
       const float4 v = *reinterpret_cast<const float4*>(
           ringA + arr + ss * kFRowB + ((ch ^ (ss & 7)) << 4));
       *reinterpret_cast<float4*>(ringA + arr + sd * kFRowB + ((ch ^ (sd & 7)) << 4)) = v;
@@ -228,8 +237,8 @@ conv_xy_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __r
     }
   };
 
-  const int grp = tid >> 6;                              // 4 row groups of 8 outputs
-  const int col = (tid & 63) * 2;                        // column pair
+  const int grp = tid / kFPairs;                         // 4 row groups of 8 outputs
+  const int col = (tid % kFPairs) * 2;                   // column pair
   uint32_t xo[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) xo[k] = (uint32_t)((((col >> 2) ^ k) << 4) + ((col & 3) << 2));
@@ -309,7 +318,7 @@ static int run_xy(const float* in, float* outC, float* outD, int Z, int Y, int X
   if (encode_tensor_map_f32(&tin, in, 3, dims, strides, box, true)) return MMB_ERR_CUDA;
   // split the marched axis when column strips x planes alone cannot fill the GPU
   const int64_t ctas = cdiv(pitch, kFCols) * Z;
-  const int64_t want = 2 * (int64_t)num_sms();
+  const int64_t want = (512 / kFThreads) * (int64_t)num_sms();
   int nseg = 1;
   if (ctas < want) {
     nseg = (int)cdiv(want, ctas);

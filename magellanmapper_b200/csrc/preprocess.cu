@@ -26,8 +26,11 @@ namespace mmb {
 
 int64_t preprocess_large_work_bytes(int Z, int Y, int64_t pitch, int bz, int by, int bx);
 
-constexpr int kPreThreads = 640;
-constexpr int kPreMinBlocks = 2;
+// CTA shapes: cubic blocks up to NL^3 run 640 threads (25 voxels per thread at 25^3); thin
+// blocks - anisotropic volumes: 5 x 25 x 25 at 5 x 1 x 1 um - get their own (NZ, NL)
+// instantiation with a CTA sized for ~20 voxels per thread, so that the per-thread loops
+// and the line sweeps of the blur keep every thread busy
+constexpr int kPreCubicThreads = 640;
 
 struct PreGeom {
   int Z, Y, X;
@@ -51,22 +54,26 @@ __device__ __forceinline__ double np_lerp(double a, double b, double t) {
   return t >= 0.5 ? b - d * (1.0 - t) : a + d * t;
 }
 
-// FULL: the block is NL x NL x NL, so every index decomposition divides by a
+// FULL: the block is NZ x NL x NL, so every index decomposition divides by a
 // compile-time constant; partial blocks at the chunk faces take the generic body.
-template <typename T, int NL, bool FULL>
+template <typename T, int NZ, int NL, bool FULL, int kPreThreads>
 __device__ __forceinline__ void preprocess_body(const T* __restrict__ in, const PreGeom& g,
                                                 const mmb_preproc_params& p,
                                                 const float* __restrict__ mats, int mat_pitch,
                                                 float* __restrict__ out, int z0, int y0, int x0,
                                                 int nz_rt, int ny_rt, int nx_rt) {
-  constexpr int NVOX = NL * NL * NL;
+  constexpr int NVOX = NZ * NL * NL;
   constexpr int NPT = (NVOX + kPreThreads - 1) / kPreThreads;
   constexpr int NVOXP = (NVOX + 3) / 4 * 4;      // keeps M 16-byte aligned for float4 rows
   constexpr int NLP = (NL + 3) / 4 * 4;          // matrix row pitch (float4 rows)
+  constexpr int NZP = (NZ + 3) / 4 * 4;
+  // blur matrices live in shared memory with rows interleaved in pairs - entry (i / 2, j)
+  // holds (m[i][j], m[i + 1][j]) - so that two outputs of a line share one packed FFMA2
+  constexpr int MZ = 2 * ((NZ + 1) / 2) * NZP, MYX = 2 * ((NL + 1) / 2) * NLP;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* vals = reinterpret_cast<float*>(smem_raw);                 // NVOX
-  float* M = vals + NVOXP;                                           // 3 * NL * NLP
-  int* hist = reinterpret_cast<int*>(M + 3 * NL * NLP);              // 2 * 256
+  float* M = vals + NVOXP;                                           // MZ + 2 * MYX
+  int* hist = reinterpret_cast<int*>(M + MZ + 2 * MYX);              // 2 * 256
   __shared__ unsigned s_prefix[2];
   __shared__ int s_k[2];
   __shared__ int s_cnt_le[2];
@@ -77,7 +84,7 @@ __device__ __forceinline__ void preprocess_body(const T* __restrict__ in, const 
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  const int nz = FULL ? NL : nz_rt, ny = FULL ? NL : ny_rt, nx = FULL ? NL : nx_rt;
+  const int nz = FULL ? NZ : nz_rt, ny = FULL ? NL : ny_rt, nx = FULL ? NL : nx_rt;
   const int n = nz * ny * nx;
   const int nyx = ny * nx;
 
@@ -91,9 +98,12 @@ __device__ __forceinline__ void preprocess_body(const T* __restrict__ in, const 
     const int lens[3] = {nz, ny, nx};
     for (int a = 0; a < 3; ++a) {
       const float* src = mats + (int64_t)(lens[a] - 1) * mat_pitch;   // matrix for length len
-      for (int i = tid; i < NL * NLP; i += kPreThreads) {
-        const int r = i / NLP, c = i - r * NLP;
-        M[a * NL * NLP + i] = (r < lens[a] && c < lens[a]) ? src[r * lens[a] + c] : 0.f;
+      const int mp = a == 0 ? NZP : NLP;
+      float* Ma = M + (a == 0 ? 0 : MZ + (a - 1) * MYX);
+      for (int i = tid; i < (a == 0 ? MZ : MYX); i += kPreThreads) {
+        const int h = i & 1, e = i >> 1, pr = e / mp, c = e - pr * mp;
+        const int r = 2 * pr + h;
+        Ma[i] = (r < lens[a] && c < lens[a]) ? src[r * lens[a] + c] : 0.f;
       }
     }
   }
@@ -123,7 +133,9 @@ __device__ __forceinline__ void preprocess_body(const T* __restrict__ in, const 
 #pragma unroll
   for (int k = 0; k < NPT; ++k) {
     const int i = tid + k * kPreThreads;
-    keys[k] = 0xffffffffu;                    // padding never counts as "< K"
+    // padding never counts as "< K" (integer keys are below 2^16: the count below takes
+    // the sign bit of key - K)
+    keys[k] = INTKEY ? 0x7fffffffu : 0xffffffffu;
     if (i < n) keys[k] = INTKEY ? (unsigned)vals[i] : key_of(vals[i]);
   }
   unsigned K0 = 0u, K1 = 0u;
@@ -135,8 +147,13 @@ __device__ __forceinline__ void preprocess_body(const T* __restrict__ in, const 
       int c0 = 0, c1 = 0;
 #pragma unroll
       for (int k = 0; k < NPT; ++k) {
-        c0 += keys[k] < T0 ? 1 : 0;
-        c1 += keys[k] < T1 ? 1 : 0;
+        if (INTKEY) {        // keys and thresholds < 2^31: the borrow is the sign of the difference
+          c0 += (int)((keys[k] - T0) >> 31);
+          c1 += (int)((keys[k] - T1) >> 31);
+        } else {
+          c0 += keys[k] < T0 ? 1 : 0;
+          c1 += keys[k] < T1 ? 1 : 0;
+        }
       }
       c0 = __reduce_add_sync(0xffffffffu, c0);
       c1 = __reduce_add_sync(0xffffffffu, c1);
@@ -203,7 +220,10 @@ __device__ __forceinline__ void preprocess_body(const T* __restrict__ in, const 
   // ---- stretch, block mean, clip --------------------------------------------
   const double vmin = s_vmin, vmax = s_vmax;
   const bool degenerate = s_degenerate != 0;
-  const double inv_den = vmax - vmin;
+  // one reciprocal per block instead of a float64 division per voxel (about 60 instructions
+  // each): at most one unit in the last place of the float64 quotient, far inside the float32
+  // rounding of the result
+  const double inv_den = 1.0 / (vmax - vmin);
   float den[NPT];
   double psum = 0.0;
 #pragma unroll
@@ -214,7 +234,7 @@ __device__ __forceinline__ void preprocess_body(const T* __restrict__ in, const 
       double s = (double)vals[i];
       if (!degenerate) {
         s = fmin(fmax(s, vmin), vmax);
-        s = (s - vmin) / inv_den;
+        s = (s - vmin) * inv_den;
       }
       psum += s;
       const double c = fmin(fmax(s, p.clip_min), p.clip_max);
@@ -236,35 +256,39 @@ __device__ __forceinline__ void preprocess_body(const T* __restrict__ in, const 
 
   // ---- sigma = 8 Gaussian, 'nearest', as three in-place matrix sweeps (z,y,x) --
   if (p.unsharp_strength != 0.0) {
-    for (int a = 0; a < 3; ++a) {
+    auto sweep = [&](auto lp_tag, int a, const float* Ma) {
+      constexpr int LP = decltype(lp_tag)::value;        // padded line length of this axis
       const int len = a == 0 ? nz : (a == 1 ? ny : nx);
       const int nlines = n / len;
-      const float* Ma = M + a * NL * NLP;
       for (int l = tid; l < nlines; l += kPreThreads) {
         int base, stride;
         if (a == 2) { base = l * nx; stride = 1; }
         else if (a == 1) { const int z = l / nx, x = l - z * nx; base = z * nyx + x; stride = nx; }
         else { base = l; stride = nyx; }
-        float v[NLP];
+        float v[LP];
 #pragma unroll
-        for (int j = 0; j < NLP; ++j) v[j] = j < len ? vals[base + j * stride] : 0.f;
+        for (int j = 0; j < LP; ++j) v[j] = j < len ? vals[base + j * stride] : 0.f;
 #pragma unroll 1
-        for (int i = 0; i < len; ++i) {
-          const float4* row = reinterpret_cast<const float4*>(Ma + i * NLP);
-          float acc = 0.f;
+        for (int i = 0; i < len; i += 2) {
+          // outputs i and i + 1 in one packed accumulator; same order of accumulation per
+          // output as a scalar loop over j
+          const float4* row = reinterpret_cast<const float4*>(Ma + i * LP);   // (i / 2) * 2 LP
+          float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int j4 = 0; j4 < NLP / 4; ++j4) {
-            const float4 m = row[j4];
-            acc = fmaf(m.x, v[4 * j4 + 0], acc);
-            acc = fmaf(m.y, v[4 * j4 + 1], acc);
-            acc = fmaf(m.z, v[4 * j4 + 2], acc);
-            acc = fmaf(m.w, v[4 * j4 + 3], acc);
+          for (int j2 = 0; j2 < LP / 2; ++j2) {
+            const float4 m = row[j2];
+            acc = __ffma2_rn(make_float2(m.x, m.y), make_float2(v[2 * j2], v[2 * j2]), acc);
+            acc = __ffma2_rn(make_float2(m.z, m.w), make_float2(v[2 * j2 + 1], v[2 * j2 + 1]), acc);
           }
-          vals[base + i * stride] = acc;
+          vals[base + i * stride] = acc.x;
+          if (i + 1 < len) vals[base + (i + 1) * stride] = acc.y;
         }
       }
       __syncthreads();
-    }
+    };
+    sweep(std::integral_constant<int, NZP>(), 0, M);
+    sweep(std::integral_constant<int, NLP>(), 1, M + MZ);
+    sweep(std::integral_constant<int, NLP>(), 2, M + MZ + MYX);
     // unsharp mask: den + (den - strength * blurred)
     const float us = (float)p.unsharp_strength;
 #pragma unroll
@@ -298,8 +322,8 @@ __device__ __forceinline__ void preprocess_body(const T* __restrict__ in, const 
   }
 }
 
-template <typename T, int NL>
-__global__ void __launch_bounds__(kPreThreads, NL <= 25 ? kPreMinBlocks : 1)
+template <typename T, int NZ, int NL, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 preprocess_kernel(const T* __restrict__ in, const __grid_constant__ PreGeom g,
                   const __grid_constant__ mmb_preproc_params p, const float* __restrict__ mats,
                   int mat_pitch, float* __restrict__ out) {
@@ -309,10 +333,12 @@ preprocess_kernel(const T* __restrict__ in, const __grid_constant__ PreGeom g,
   const int bzi = b;
   const int z0 = bzi * g.bz, y0 = byi * g.by, x0 = bxi * g.bx;
   const int nz = min(g.bz, g.Z - z0), ny = min(g.by, g.Y - y0), nx = min(g.bx, g.X - x0);
-  if (nz == NL && ny == NL && nx == NL)       // CTA-uniform
-    preprocess_body<T, NL, true>(in, g, p, mats, mat_pitch, out, z0, y0, x0, nz, ny, nx);
+  if (nz == NZ && ny == NL && nx == NL)       // CTA-uniform
+    preprocess_body<T, NZ, NL, true, THREADS>(in, g, p, mats, mat_pitch, out, z0, y0, x0, nz, ny,
+                                              nx);
   else
-    preprocess_body<T, NL, false>(in, g, p, mats, mat_pitch, out, z0, y0, x0, nz, ny, nx);
+    preprocess_body<T, NZ, NL, false, THREADS>(in, g, p, mats, mat_pitch, out, z0, y0, x0, nz,
+                                               ny, nx);
 }
 
 // dense matrices of scipy.ndimage.gaussian_filter1d(sigma=8, truncate=4,
@@ -351,13 +377,15 @@ static const float* blur_matrices(int device, int* pitch_out) {
   return d;
 }
 
-template <typename T, int NL>
+template <typename T, int NZ, int NL, int THREADS, int MINB>
 static int launch_pre(const void* in, const PreGeom& g, const mmb_preproc_params& p,
                       const float* mats, int mat_pitch, float* out, cudaStream_t st) {
-  constexpr int NLP = (NL + 3) / 4 * 4;
-  const size_t smem = (size_t)((NL * NL * NL + 3) / 4 * 4) * 4 + (size_t)3 * NL * NLP * 4 + 512 * 4;
+  constexpr int NLP = (NL + 3) / 4 * 4, NZP = (NZ + 3) / 4 * 4;
+  const size_t smem = (size_t)((NZ * NL * NL + 3) / 4 * 4) * 4 +
+                      (size_t)(2 * ((NZ + 1) / 2) * NZP + 2 * 2 * ((NL + 1) / 2) * NLP) * 4 +
+                      512 * 4;
   static bool configured = false;
-  auto kern = preprocess_kernel<T, NL>;
+  auto kern = preprocess_kernel<T, NZ, NL, THREADS, MINB>;
   if (!configured) {
     MMB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));
@@ -365,7 +393,7 @@ static int launch_pre(const void* in, const PreGeom& g, const mmb_preproc_params
   }
   const int64_t nblocks = (int64_t)g.nbz * g.nby * g.nbx;
   ProfScope ps(PROF_PREPROCESS, (double)g.Z * g.Y * g.X, st);
-  kern<<<(unsigned)nblocks, kPreThreads, smem, st>>>((const T*)in, g, p, mats, mat_pitch, out);
+  kern<<<(unsigned)nblocks, THREADS, smem, st>>>((const T*)in, g, p, mats, mat_pitch, out);
   MMB_CHECK_LAUNCH();
   return MMB_OK;
 }
@@ -374,10 +402,16 @@ template <typename T>
 static int dispatch_nl(const void* in, const PreGeom& g, const mmb_preproc_params& p,
                        const float* mats, int mat_pitch, float* out, cudaStream_t st) {
   const int m = g.bz > g.by ? (g.bz > g.bx ? g.bz : g.bx) : (g.by > g.bx ? g.by : g.bx);
-  if (m <= 8) return launch_pre<T, 8>(in, g, p, mats, mat_pitch, out, st);
-  if (m <= 16) return launch_pre<T, 16>(in, g, p, mats, mat_pitch, out, st);
-  if (m <= 25) return launch_pre<T, 25>(in, g, p, mats, mat_pitch, out, st);
-  return launch_pre<T, 32>(in, g, p, mats, mat_pitch, out, st);
+  const int myx = g.by > g.bx ? g.by : g.bx;
+  if (m <= 8) return launch_pre<T, 8, 8, kPreCubicThreads, 2>(in, g, p, mats, mat_pitch, out, st);
+  // thin blocks of anisotropic volumes (z resolution coarser than y, x)
+  if (g.bz <= 5 && myx > 8 && myx <= 25)
+    return launch_pre<T, 5, 25, 160, 6>(in, g, p, mats, mat_pitch, out, st);
+  if (g.bz <= 8 && myx > 8 && myx <= 25)
+    return launch_pre<T, 8, 25, 256, 4>(in, g, p, mats, mat_pitch, out, st);
+  if (m <= 16) return launch_pre<T, 16, 16, kPreCubicThreads, 2>(in, g, p, mats, mat_pitch, out, st);
+  if (m <= 25) return launch_pre<T, 25, 25, kPreCubicThreads, 2>(in, g, p, mats, mat_pitch, out, st);
+  return launch_pre<T, 32, 32, kPreCubicThreads, 1>(in, g, p, mats, mat_pitch, out, st);
 }
 
 int preprocess_large_impl(const void* in, int dtype, const int64_t strides[3], int Z, int Y,

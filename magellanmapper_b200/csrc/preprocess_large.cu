@@ -189,7 +189,7 @@ lg_stretch_kernel(const T* __restrict__ in, const __grid_constant__ LgGeom g, do
   lg_block_box(g, b, lo, n3);
   const double vmin = blk[b].vmin, vmax = blk[b].vmax;
   const bool degenerate = blk[b].degenerate != 0;
-  const double den_d = vmax - vmin;
+  const double den_d = 1.0 / (vmax - vmin);      // as the shared-memory kernel: one reciprocal
   const long long n = (long long)n3[0] * n3[1] * n3[2];
   const int nyx = n3[1] * n3[2];
   double psum = 0.0;
@@ -201,7 +201,7 @@ lg_stretch_kernel(const T* __restrict__ in, const __grid_constant__ LgGeom g, do
                           (int64_t)(lo[2] + x) * g.sx];
     if (!degenerate) {
       s = fmin(fmax(s, vmin), vmax);
-      s = (s - vmin) / den_d;
+      s = (s - vmin) * den_d;
     }
     psum += s;
     den[((int64_t)(lo[0] + z) * g.Y + (lo[1] + y)) * g.pitch + (lo[2] + x)] =

@@ -154,6 +154,33 @@ def test_log_scale_matches_scipy(gpu, shape, seed):
     assert worst < REL_TOL
 
 
+@pytest.mark.parametrize("shape", [(9, 70, 140), (3, 64, 33), (5, 505, 505), (12, 200, 48),
+                                   (2, 97, 300), (40, 66, 129)])
+@pytest.mark.parametrize("sigma", [1.9, 3.0, 4.0, 4.6, 5.0])
+def test_fused_xy_sweep_equals_separate_sweeps(gpu, shape, sigma):
+    """The fused x -> y sweep (log_xy.cu; radii <= 20, y extent >= 64) inside
+    ``mmb_log_scale`` against the three separate sweeps of ``mmb_log_pass``: same
+    accumulation order per output, so the LoG volumes are equal BIT FOR BIT; and against
+    scipy within 1e-4.  Shapes cover ragged last tiles in x and y, pitch > X padding, planes
+    too few to fill the GPU (the y axis is then cut into segments), radii of every ring
+    geometry (RP = 8, 16, 24)."""
+    rng = np.random.default_rng(int(sigma * 10) + shape[1])
+    a = rng.random(shape, dtype=np.float32)
+    a[rng.random(shape) < 0.01] += 3.0
+    f = _vol_to_dev(gpu, a)
+    X = shape[2]
+    fused = gpu.log_scale(f, X, sigma)
+    A, B = gpu.log_pass(f, None, X, 2, 0, sigma)
+    C, D = gpu.log_pass(A, B, X, 1, 1, sigma)
+    sep, _ = gpu.log_pass(C, D, X, 0, 2, sigma, scale=-(sigma * sigma))
+    torch.cuda.synchronize()
+    got, want = fused[:, :, :X].cpu().numpy(), sep[:, :, :X].cpu().numpy()
+    assert np.isfinite(got).all()
+    np.testing.assert_array_equal(got, want)
+    ref = -ndi.gaussian_laplace(a.astype(np.float64), sigma) * sigma ** 2
+    assert _rel_err(got, ref) < REL_TOL
+
+
 # ---------------------------------------------------------------- local max
 
 def _gpu_cube(gpu, f, X, sigmas):

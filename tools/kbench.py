@@ -104,6 +104,13 @@ def main():
         ms = timeit(lambda: lp(C, D, O, None, 0, 2, sigma), args.reps)
         report(f"log_z r={r}", ms, 12.0, 4 * r + 2, nv_p)
 
+        def fused():
+            rc = lib.mmb_log_xy_fused(gpu._ptr(F), gpu._ptr(C), gpu._ptr(D), Z, Y, X, pitch,
+                                      float(sigma), gpu._stream())
+            assert rc == 0, lib.mmb_last_error()
+        ms = timeit(fused, args.reps)
+        report(f"log_xy fused r={r}", ms, 12.0, 10 * r + 5, nv_p)
+
     # local maxima on a real 3-scale neighbourhood
     sig = np.linspace(3, 5, 10)
     work = torch.zeros(lib.mmb_log_work_bytes(Z, Y, pitch), dtype=torch.uint8, device=dev)
