@@ -270,7 +270,7 @@ __device__ __forceinline__ void scatter_rows_ring(const float* const (&b0)[NBLK]
 }
 
 template <int R, int MODE, int NB, int G, int COLS>
-__global__ void __launch_bounds__(G * COLS / 2, 2)
+__global__ void __launch_bounds__(G * COLS / 2, 512 / (G * COLS / 2))
 conv_march_kernel(const float* __restrict__ in0, const float* __restrict__ in1,
                   float* __restrict__ out0, float* __restrict__ out1, int n_axis,
                   int64_t inner, int64_t outer_stride, const __grid_constant__ LogWeights w,

@@ -7,6 +7,10 @@ constexpr int kNB = 16;
 constexpr int kThreads = 128;
 
 constexpr int kCols = 128;
+#ifndef MMB_MARCH_COLS
+#define MMB_MARCH_COLS 64
+#endif
+constexpr int kMarchCols = MMB_MARCH_COLS;     // columns per CTA of the marching kernel
 constexpr int kTileThreads = 256;
 
 template <int R>
@@ -21,8 +25,8 @@ static int run(const float* in0, const float* in1, float* out0, float* out1, int
     if (aligned) {
       // marching kernel: ring of 2*RP + 2*STEP rows of both inputs, 2 CTAs per SM
       constexpr int G = MMB_MARCH_G, NBM = MMB_MARCH_NB;
-      constexpr size_t smem = (size_t)2 * (2 * ((R + 7) / 8 * 8) + 2 * NBM * G) * kCols * sizeof(float);
-      auto kern = conv_march_kernel<R, 1, NBM, G, kCols>;
+      constexpr size_t smem = (size_t)2 * (2 * ((R + 7) / 8 * 8) + 2 * NBM * G) * kMarchCols * sizeof(float);
+      auto kern = conv_march_kernel<R, 1, NBM, G, kMarchCols>;
       static bool configured = false;
       if (!configured) {
         MMB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -32,8 +36,8 @@ static int run(const float* in0, const float* in1, float* out0, float* out1, int
       // split the marched axis when columns x outer slices alone cannot fill the GPU
       // (thin chunks, small ROIs): segments of a multiple of STEP rows, >= 4 steps each
       constexpr int STEP = NBM * G;
-      const int64_t ctas = cdiv(inner, kCols) * outer;
-      const int64_t want = 2 * (int64_t)num_sms();
+      const int64_t ctas = cdiv(inner, kMarchCols) * outer;
+      const int64_t want = (512 / (G * kMarchCols / 2)) * (int64_t)num_sms();
       int nseg = 1;
       if (ctas < want) {
         nseg = (int)cdiv(want, ctas);
@@ -42,8 +46,8 @@ static int run(const float* in0, const float* in1, float* out0, float* out1, int
         if (nseg < 1) nseg = 1;
       }
       const int seg_len = (int)cdiv(cdiv(n_axis, nseg), STEP) * STEP;
-      dim3 grid((unsigned)cdiv(inner, kCols), (unsigned)cdiv(n_axis, seg_len), (unsigned)outer);
-      kern<<<grid, G * kCols / 2, smem, st>>>(in0, in1, out0, out1, n_axis, inner,
+      dim3 grid((unsigned)cdiv(inner, kMarchCols), (unsigned)cdiv(n_axis, seg_len), (unsigned)outer);
+      kern<<<grid, G * kMarchCols / 2, smem, st>>>(in0, in1, out0, out1, n_axis, inner,
                                               (int64_t)n_axis * inner, w, scale, seg_len);
       MMB_CHECK_LAUNCH();
       return MMB_OK;

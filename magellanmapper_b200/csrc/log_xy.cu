@@ -21,13 +21,14 @@
 // A and B never leave the SM: the kernel reads 4 B/voxel (plus the x halo, an L2 hit) and
 // writes 8, and is bound by the FP32 pipe alone ((10 r + 5) lane-FMAs per voxel).
 //
-// Ring: RR = 2 RP + 32 rows of A and of B (RP = R rounded up to 8), row pitch 512 B, 16-byte
+// Ring: RR = 2 RP + 32 rows of A and of B (RP = R rounded up to 4), row pitch 512 B, 16-byte
 // chunks XOR-swizzled with (slot & 7) so that both the x phase's stores (lane = row) and the
 // y phase's loads (lane = column pair) are bank-conflict free.  Slot of row q is
 // (q - (a - RP)) mod RR, a = first output row of the CTA's segment.  The y phase's windows
 // start at multiples of 8 slots, so an 8-row block never straddles the ring end and its
 // swizzle key is a compile-time constant.  Rows outside [0, Y) are 'reflect' copies of rows
 // inside, made in shared memory after the x phase that produced their sources.
+#include <stdlib.h>
 #include "log_kernels.cuh"
 #include "tma.cuh"
 
@@ -63,7 +64,8 @@ __device__ __forceinline__ int x_sw_off_f(int rr, int p) {
 template <int R>
 struct FGeom {
   static constexpr int R4 = (R + 3) / 4 * 4;
-  static constexpr int RP = (R + 7) / 8 * 8;
+  // ring halo: R rounded up to 4 keeps RR and the y window (8 + 2 RP rows) multiples of 8
+  static constexpr int RP = (R + 3) / 4 * 4;
   static constexpr int WIN = kFCols + 2 * R4;          // x window of a tile, floats
   static constexpr int NBOX = (WIN + 31) / 32;
   static constexpr int W = 16 + 2 * R4;                // per-thread x window, floats
@@ -339,7 +341,12 @@ static int run_xy(const float* in, float* outC, float* outD, int Z, int Y, int X
 int launch_xy_fused(int r, const float* in, float* outC, float* outD, int Z, int Y, int X,
                     int64_t pitch, const LogWeights& w, cudaStream_t st) {
   const uintptr_t bits = (uintptr_t)in | (uintptr_t)outC | (uintptr_t)outD;
-  if (r > 20 || (bits & 15) != 0 || pitch % 4 != 0 || X < 32 || Y < 64 || Z > 65535)
+  // measured on a 505^3 chunk (profiles/r02_kbench.jsonl): fused vs x + y sweeps 0.63 vs
+  // 0.71 ms at r = 12, 0.80 vs 0.84 at r = 16, 1.02 vs 0.99 at r = 20 - the saving of the A, B
+  // round trip shrinks as the arithmetic grows, and the longer prologue (two x tiles above
+  // r = 16) turns it into a loss around r = 19
+  static const int r_max = getenv("MMB_XY_RMAX") ? atoi(getenv("MMB_XY_RMAX")) : 18;
+  if (r > r_max || r > 20 || (bits & 15) != 0 || pitch % 4 != 0 || X < 32 || Y < 64 || Z > 65535)
     return MMB_ERR_UNSUPPORTED;
 #define XY_(RR) if (r <= RR) return run_xy<RR>(in, outC, outD, Z, Y, X, pitch, w, st);
   MMB_XY_BUCKETS(XY_)

@@ -95,7 +95,8 @@ def main():
                               pitch, axis, mode, float(sigma), -sigma * sigma, gpu._stream())
         assert rc == 0, lib.mmb_last_error()
 
-    for sigma in ((4.111111111111111,) if args.ncu else (3.0, 4.111111111111111, 5.0)):
+    os.environ.setdefault("MMB_XY_RMAX", "20")       # time the fused sweep at every radius
+    for sigma in ((4.111111111111111,) if args.ncu else (3.0, 4.111111111111111, 4.5, 5.0)):
         r = int(4 * sigma + 0.5)
         ms = timeit(lambda: lp(F, None, A, B, 2, 0, sigma), args.reps)
         report(f"log_x r={r}", ms, 12.0, 4 * r + 2)
