@@ -298,6 +298,46 @@ def gen_iso_unmix(ns):
     np.savez_compressed(os.path.join(OUT, "iso_unmix.npz"), **out)
 
 
+def gen_sinks(ns):
+    """The reference's CSV and SQLite sinks fed with a detector table: the CSV text, the
+    database schema and the stored blob rows (incl. the replace-on-duplicate rule)."""
+    import gzip
+    import importlib
+    import sqlite3
+    export_rois = importlib.import_module("magmap.io.export_rois")
+    ref_sqlite = importlib.import_module("magmap.io.sqlite")
+    g = np.load(os.path.join(OUT, "detect_small.npz"))
+    blobs = g["raw"].copy()
+    blobs[::3, 4] = 1            # some confirmed
+    blobs[1::4, 5] = 0
+    dup = np.vstack([blobs, blobs[:5] * [1, 1, 1, 2, 1, 1, 1, 1, 1, 1, 1]])   # same key, new radius
+    out = {"blobs": dup}
+    with tempfile.TemporaryDirectory() as td:
+        export_rois.blobs_to_csv(dup, os.path.join(td, "img.npy"))
+        with gzip.open(os.path.join(td, "img_blobs.csv.gz"), "rb") as f:
+            out["csv"] = np.frombuffer(f.read(), dtype=np.uint8)
+        conn, cur = ref_sqlite._create_db(os.path.join(td, "magmap.db"))
+        exp_id = ref_sqlite.insert_experiment(conn, cur, "synth", None)
+        roi_id, _ = ref_sqlite.select_or_insert_roi(conn, cur, exp_id, None, (5, 6, 7), (64, 64, 40))
+        roi_again, _ = ref_sqlite.select_or_insert_roi(conn, cur, exp_id, 0, (5, 6, 7), (64, 64, 40))
+        assert roi_id == roi_again
+        ref_sqlite.insert_blobs(conn, cur, roi_id, dup[:, :7])
+        n_del = ref_sqlite.delete_blobs(conn, cur, roi_id, dup[7:9])
+        cur.execute("SELECT {} FROM blobs ORDER BY id".format(ref_sqlite._COLS_BLOBS))
+        out["rows"] = np.array([list(r) for r in cur.fetchall()], dtype=np.float64)
+        out["n_deleted"] = np.array(n_del)
+        out["confirmed1"] = ref_sqlite.select_blobs_confirmed(cur, 1)
+        cur.execute("SELECT name, sql FROM sqlite_master WHERE type = 'table' AND name NOT LIKE "
+                    "'sqlite_%' ORDER BY name")
+        out["schema"] = np.array(["{}|{}".format(r[0], " ".join(r[1].split()))
+                                  for r in cur.fetchall()], dtype=str)
+        cur.execute("SELECT experiment_id, series, offset_x, offset_y, offset_z, size_x, size_y, "
+                    "size_z FROM rois")
+        out["rois"] = np.array([list(r) for r in cur.fetchall()], dtype=np.int64)
+        conn.close()
+    np.savez_compressed(os.path.join(OUT, "sinks.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_shim.load_reference()
@@ -310,6 +350,7 @@ def main():
     gen_detect_small(ns)
     gen_stack_small(ns)
     gen_iso_unmix(ns)
+    gen_sinks(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -299,3 +299,39 @@ def test_calc_near_intensity_bounds_list_semantics(golden_dir):
     np.testing.assert_array_equal(mins, g["u16_2c_near_mins"])
     np.testing.assert_array_equal(maxs, g["u16_2c_near_maxs"])
     assert importer.calc_near_intensity_bounds([3.0], [4.0], [], []) == ([3.0], [4.0])
+
+
+def test_csv_and_sqlite_sinks_match_reference(golden_dir, tmp_path):
+    """``export_rois.blobs_to_csv`` and the blob tables of ``sqlite`` against files written
+    by the unmodified reference: CSV text, schema, stored rows, replace-on-duplicate,
+    delete, ROI select-or-insert."""
+    import gzip
+    from magellanmapper_b200.io import export_rois, sqlite
+    g = np.load(os.path.join(golden_dir, "sinks.npz"))
+    blobs = g["blobs"]
+    out = export_rois.blobs_to_csv(blobs, str(tmp_path / "img.npy"))
+    assert out.endswith("img_blobs.csv.gz")
+    with gzip.open(out, "rb") as f:
+        assert f.read() == g["csv"].tobytes()
+    conn, cur = sqlite.create_db(str(tmp_path / "magmap.db"))
+    exp_id = sqlite.insert_experiment(conn, cur, "synth")
+    roi_id, _ = sqlite.select_or_insert_roi(conn, cur, exp_id, None, (5, 6, 7), (64, 64, 40))
+    again, msg = sqlite.select_or_insert_roi(conn, cur, exp_id, 0, (5, 6, 7), (64, 64, 40))
+    assert again == roi_id and msg.startswith("Found")
+    sqlite.insert_blobs(conn, cur, roi_id, blobs[:, :7])
+    assert sqlite.delete_blobs(conn, cur, roi_id, blobs[7:9]) == int(g["n_deleted"])
+    cur.execute("SELECT {} FROM blobs ORDER BY id".format(sqlite._COLS_BLOBS))
+    rows = np.array([list(r) for r in cur.fetchall()], dtype=np.float64)
+    np.testing.assert_array_equal(rows, g["rows"])
+    np.testing.assert_array_equal(sqlite.select_blobs_confirmed(cur, 1), g["confirmed1"])
+    cur.execute("SELECT name, sql FROM sqlite_master WHERE type = 'table' AND name NOT LIKE "
+                "'sqlite_%' ORDER BY name")
+    schema = ["{}|{}".format(r[0], " ".join(r[1].split())) for r in cur.fetchall()]
+    norm = lambda t: str(t).replace(", ", ",")            # same SQL up to blanks after commas
+    assert [norm(t) for t in schema] == [norm(t) for t in g["schema"]]
+    cur.execute("SELECT experiment_id, series, offset_x, offset_y, offset_z, size_x, size_y, "
+                "size_z FROM rois")
+    np.testing.assert_array_equal(np.array([list(r) for r in cur.fetchall()]), g["rois"])
+    got, ids = sqlite.select_blobs_by_roi(cur, roi_id)
+    assert got.shape == (len(rows), 7) and len(ids) == len(rows)
+    conn.close()
