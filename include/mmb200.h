@@ -287,6 +287,21 @@ int mmb_stack_tables(const mmb_row* rows, int n, const mmb_stack_geom* geom, int
                      double* out_table, int32_t* n_out, int32_t* seam_counts, void* work,
                      void* stream);
 
+/* ---- intensity co-localisation ----------------------------------------------
+ * The voxel work of colocalizer.colocalize_blobs (magmap/cv/colocalizer.py:340-441):
+ * for every channel, every blob of that channel owns the voxels of its
+ * skimage.morphology.ball(2) neighbourhood that no blob of the same channel with a
+ * larger index reaches (the grey dilation of the index-labelled mask); the ROI
+ * intensities of the owned voxels are summed for EVERY channel.  `roi`: (z, y, x, c)
+ * with element strides; `blobs`: (n, 4) int32 rows z, y, x, channel (all inside the
+ * ROI); outputs `sums` (n, C) float64 and `counts` (n) int32, so that the reference's
+ * np.mean(roi[mask == b, c]) is sums[b][c] / counts[b].  Integer ROIs are summed
+ * exactly.  `work`: mmb_coloc_work_bytes bytes.                                    */
+int64_t mmb_coloc_work_bytes(int Z, int Y, int X);
+int mmb_coloc_sums(const void* roi, int dtype, const int64_t strides[4], int Z, int Y, int X,
+                   int C, const int32_t* blobs, int n, double* sums, int32_t* counts,
+                   void* work, void* stream);
+
 /* number of kernels this library has launched in this process (bench.py's
  * gpu_launches).                                                              */
 int64_t mmb_launch_count(void);

@@ -79,6 +79,9 @@ SIGNATURES = {
                                     C.c_int, C.c_int, C.c_int64, C.c_int, _vp]),
     "mmb_unmix_subtract": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int64,
                                      C.c_double, _vp]),
+    "mmb_coloc_work_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
+    "mmb_coloc_sums": (C.c_int, [_vp, C.c_int, C.c_int64 * 4, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 _vp, C.c_int, _vp, _vp, _vp, _vp]),
     "mmb_log_work_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int64]),
     "mmb_log_scale": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int64,
                                 C.c_double, _vp]),

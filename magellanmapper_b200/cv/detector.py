@@ -394,8 +394,30 @@ def detection_shape(shape: Sequence[int], channels: Sequence[int]) -> Tuple[int,
     return cv_nd.isotropic_shape(shape, isotropic)
 
 
+def preprocessed_roi(roi, multichannel: bool, denoise_max_shape: Sequence[int]):
+    """Every channel of an ROI preprocessed block by block (stack_detect.py:122-150) into one
+    dense ``(z, y, x[, c])`` float32 CUDA tensor: what the reference hands to ``detect_blobs``
+    and to ``colocalize_blobs`` (as float64)."""
+    import torch
+    from .. import gpu
+    shape = tuple(int(v) for v in roi.shape[:3])
+    block = tuple(int(v) for v in denoise_max_shape)
+    n_chl = int(roi.shape[3]) if multichannel else 1
+    out = torch.empty(shape + ((n_chl,) if multichannel else ()), dtype=torch.float32,
+                      device=gpu.require_cuda())
+    for c in range(n_chl):
+        src = gpu.as_source(roi, c if multichannel else None)
+        vol = gpu.preprocess_blocks(src, block, plot_3d.preproc_params(config.get_roi_profile(c), c))
+        if multichannel:
+            out[..., c] = vol[:, :, :shape[2]]
+        else:
+            out.copy_(vol[:, :, :shape[2]])
+    return out
+
+
 def enqueue_detection(det, roi, channels: Sequence[int], multichannel: bool,
-                      denoise_max_shape: Optional[Sequence[int]] = None):
+                      denoise_max_shape: Optional[Sequence[int]] = None,
+                      as_float64: bool = False):
     """Launch, without waiting, everything ``detect_blobs`` does to an ROI up to and
     including ``blob_log``, one fused chunk launch per channel on ``det`` (a
     ``gpu.ChunkDetector`` that fits ``detection_shape``).  With ``denoise_max_shape``
@@ -405,7 +427,9 @@ def enqueue_detection(det, roi, channels: Sequence[int], multichannel: bool,
     The common case is ONE launch per channel reading the caller's array in place.
     Profiles with ``isotropic`` (detector.py:893-897) or ``spectral_unmixing``
     (:910-921) go through intermediate float volumes instead: preprocess ->
-    ``mmb_resize_linear`` -> ``mmb_unmix_subtract`` -> detection."""
+    ``mmb_resize_linear`` -> ``mmb_unmix_subtract`` -> detection.  ``as_float64``: the
+    float32 ``roi`` stands for a float64 array of the reference (``preprocessed_roi``), so
+    the sigma ladder is built in float64."""
     from .. import gpu
     from . import cv_nd
     scale = calc_scaling_factor()[2]
@@ -421,7 +445,7 @@ def enqueue_detection(det, roi, channels: Sequence[int], multichannel: bool,
             settings = config.get_roi_profile(chl)
             src = gpu.as_source(roi, chl if multichannel else None)
             pre, in_scale = None, 1.0
-            f32 = src.dtype == gpu._lib.MMB_F32
+            f32 = src.dtype == gpu._lib.MMB_F32 and not as_float64
             if denoise_max_shape is not None:
                 pre = plot_3d.preproc_params(settings, chl)
                 f32 = False      # preprocessing yields float64 in the reference
@@ -447,7 +471,7 @@ def enqueue_detection(det, roi, channels: Sequence[int], multichannel: bool,
         if c not in cache:
             src = gpu.as_source(roi, c if multichannel else None)
             int_scale = {gpu._lib.MMB_U8: 1 / 255.0, gpu._lib.MMB_U16: 1 / 65535.0}.get(src.dtype)
-            f32 = src.dtype == gpu._lib.MMB_F32
+            f32 = src.dtype == gpu._lib.MMB_F32 and not as_float64
             if denoise_max_shape is not None:
                 vol = gpu.preprocess_blocks(
                     src, block, plot_3d.preproc_params(config.get_roi_profile(c), c))

@@ -164,21 +164,29 @@ class StackDetector(object):
         for it; ``finish_sub_roi`` turns the returned handle into the blob
         table.  Splitting the two lets the table assembly of one sub-ROI
         overlap the kernels of the next."""
-        from .. import gpu
-        if coloc:
-            raise NotImplementedError("intensity co-localisation is outside the accelerated path")
         shape = tuple(sub_roi.shape)
         multichannel, channels = plot_3d.setup_channels(sub_roi, channel, 3)
         channels = list(channels)
         if det is None:
             det = cls._workspace(detector.detection_shape(shape, channels))
-        tickets = detector.enqueue_detection(det, sub_roi, channels, multichannel,
-                                             denoise_max_shape)
-        return (coord, offset, last_coord, exclude_border, shape, det, tickets)
+        coloc_roi = None
+        if coloc:
+            # co-localisation reads the preprocessed intensities of EVERY channel after the
+            # detection (stack_detect.py:153-156): preprocess once into a tensor that both
+            # steps use instead of fusing the preprocessing into each channel's launch
+            coloc_roi = sub_roi
+            if denoise_max_shape is not None:
+                coloc_roi = detector.preprocessed_roi(sub_roi, multichannel, denoise_max_shape)
+            tickets = detector.enqueue_detection(det, coloc_roi, channels, multichannel, None,
+                                                 as_float64=denoise_max_shape is not None)
+        else:
+            tickets = detector.enqueue_detection(det, sub_roi, channels, multichannel,
+                                                 denoise_max_shape)
+        return (coord, offset, last_coord, exclude_border, shape, det, tickets, coloc_roi)
 
     @classmethod
     def finish_sub_roi(cls, pending) -> Tuple[Sequence[int], Optional[np.ndarray]]:
-        coord, offset, last_coord, exclude_border, shape, det, tickets = pending
+        coord, offset, last_coord, exclude_border, shape, det, tickets, coloc_roi = pending
         tables = []
         chls = [t[0] for t in tickets]
         det_shape = detector.detection_shape(shape, chls) if chls else shape
@@ -194,6 +202,11 @@ class StackDetector(object):
             exclude[0, np.equal(coord, 0)] = 0
             exclude[1, np.equal(coord, last_coord)] = 0
             segments = detector.get_blobs_interior(segments, shape, *exclude)
+        if coloc_roi is not None and segments is not None:
+            from . import colocalizer
+            colocs = colocalizer.colocalize_blobs(coloc_roi, segments)
+            if colocs is not None:
+                segments = np.hstack((segments, colocs))
         if segments is not None:
             detector.Blobs.shift_blob_rel_coords(segments, offset)
             detector.Blobs.shift_blob_abs_coords(segments, offset)
@@ -289,7 +302,7 @@ class StackDetector(object):
         closed = set()                 # strips with nothing left to enqueue
 
         def finish_oldest():
-            (coord, offset, _, _, shape, det_, tickets), strip = pending.popleft()
+            (coord, offset, _, _, shape, det_, tickets, _), strip = pending.popleft()
             rank_in_grid = int(np.ravel_multi_index(coord, grid))
             for chl, sigmas, ticket in tickets:
                 cand, _ = det_.collect_device(ticket)
@@ -618,15 +631,20 @@ def detect_blobs_blocks(filename_base: str, img5d: np_io.Image5d,
                                cols=list(device_tables.FINAL_COLS))
     else:
         blobs = detector.Blobs(segments_all, path=filename_blobs)
+    colocs = None
     if segments_all is not None and not final_on_device:
         # the abs columns carried the seam-averaged positions; they become the
         # coordinates and the helper columns go away (stack_detect.py:458-467)
         blobs.replace_rel_with_abs_blob_coords(segments_all)
         blobs.blobs = segments_all
+        if coloc:
+            # the reference slices from column 10 (stack_detect.py:463), i.e. the `region`
+            # column and all but the last co-localisation column: kept as it is
+            colocs = segments_all[:, 10:10 + n_chl].astype(np.uint8)
         segments_all = blobs.remove_abs_blob_coords(True)
 
     blobs.blobs = segments_all
-    blobs.colocalizations = None
+    blobs.colocalizations = colocs
     blobs.resolutions = config.resolutions
     blobs.basename = os.path.basename(config.filename) if config.filename else None
     blobs.roi_offset = offset

@@ -83,3 +83,83 @@ def calc_near_bounds(image, dim_channel: int = 3):
     records them: per-plane 0.5 / 99.5 percentiles reduced over the planes."""
     lows, highs = calc_plane_bounds(image, dim_channel=dim_channel)
     return calc_near_intensity_bounds([], [], lows, highs)
+
+
+# ---- image + metadata files (importer.py:272-301, 482-522, 606-745) -----------------
+
+#: version number written into the metadata file (importer.py:69)
+IMAGE5D_NP_VER = 15
+
+
+def make_filenames(filename: str, keep_ext: bool = False) -> Tuple[str, str]:
+    """``(<base>_image5d.npy, <base>_meta.yml)`` for an image path (importer.py:272-301;
+    no series / modifier, which the detection path never sets)."""
+    import os
+    from . import libmag
+    from ..settings import config
+    base = filename if keep_ext else os.path.splitext(filename)[0]
+    return (base + "_" + config.SUFFIX_IMAGE5D, base + "_" + config.SUFFIX_META)
+
+
+def _primitive(val):
+    """Numpy scalars / arrays / tuples -> Python primitives and lists (yaml_io.save_yaml
+    with ``use_primitives``)."""
+    if isinstance(val, dict):
+        return {k: _primitive(v) for k, v in val.items()}
+    if isinstance(val, (list, tuple, np.ndarray)):
+        return [_primitive(v) for v in val]
+    try:
+        return val.item()
+    except AttributeError:
+        return val
+
+
+def save_image_info(filename_meta: str, names, sizes, resolutions, magnification, zoom,
+                    near_min, near_max, scaling=None, plane=None) -> dict:
+    """Write the image metadata as the reference's ``*_meta.yml`` (importer.py:482-522)."""
+    import yaml
+    data = _primitive({
+        "ver": IMAGE5D_NP_VER, "names": names, "sizes": sizes, "resolutions": resolutions,
+        "magnification": magnification, "zoom": zoom, "near_min": near_min,
+        "near_max": near_max, "scaling": scaling, "plane": plane})
+    with open(filename_meta, "w") as f:
+        yaml.dump(data, f)
+    return data
+
+
+def load_metadata(path: str, img5d=None):
+    """Read ``*_meta.yml`` (or the older ``.npz`` next to it) and assign resolutions,
+    magnification, zoom, ``near_min`` and ``near_max`` to ``config`` (importer.py:606-745).
+    Returns ``(metadata dict or None, version number or -1)``."""
+    import os
+    import yaml
+    from . import np_io
+    from ..settings import config
+    try:
+        with open(path) as f:
+            docs = list(yaml.load_all(f, Loader=yaml.FullLoader))
+        output = docs[0] if docs else None
+    except FileNotFoundError:
+        try:
+            output = np_io.read_np_archive(np.load(f"{os.path.splitext(path)[0]}.npz"))
+        except FileNotFoundError:
+            return None, -1
+    if not output:
+        return None, -1
+    ver = output.get("ver", -1)
+    ver = int(ver) if ver is not None else -1
+    if img5d is not None:
+        img5d.meta = output
+        if "sizes" in output:
+            img5d.shapes = output["sizes"]
+    if output.get("resolutions") is not None:
+        config.resolutions = np.array(output["resolutions"])
+    if "magnification" in output:
+        config.magnification = output["magnification"]
+    if "zoom" in output:
+        config.zoom = output["zoom"]
+    if output.get("near_min") is not None:
+        config.near_min = output["near_min"]
+    if output.get("near_max") is not None:
+        config.near_max = output["near_max"]
+    return output, ver

@@ -1,4 +1,9 @@
-"""``Image5d`` container and archive reader (``magmap/io/np_io.py:33-71,159-177``)."""
+"""``Image5d`` container, archive reader and the ``.npy`` image feed of
+``magmap/io/np_io.py`` (``:33-71, 159-177, 193-592, 787-862``): an imported image is an
+``<base>_image5d.npy`` file opened as a read-only memory map plus a ``<base>_meta.yml`` file
+with resolutions and the per-channel ``near_min`` / ``near_max`` the preprocessing needs.
+The stack detector streams such a map to the GPU strip by strip (``gpu.StripFeeder``); it is
+never read into host memory whole."""
 from __future__ import annotations
 
 from typing import Any, Dict, Optional, Sequence
@@ -31,3 +36,69 @@ def read_np_archive(archive) -> Dict[str, Any]:
         except ValueError:
             print(f"unable to load {key} from archive, will ignore")
     return out
+
+
+def setup_images(path: str, series=None, subimg_offset=None, subimg_size=None) -> Image5d:
+    """Open the imported image of ``path`` for detection (the ``.npy`` route of
+    np_io.py:193-592): memory-map ``<base>_image5d.npy`` read-only, load
+    ``<base>_meta.yml`` into ``config`` (resolutions, ``near_min`` / ``near_max``,
+    magnification, zoom) and set ``config.filename``.  With ``subimg_offset`` /
+    ``subimg_size`` (z, y, x) the returned image is that view of the map, as the saved
+    sub-image route (:283-296) would hand over.
+
+    Raises:
+        FileNotFoundError: if the image file does not exist (other formats - TIFF, CZI
+            import - are outside the accelerated path).
+    """
+    import os
+    from . import importer
+    from ..settings import config
+    base = path
+    for suffix in ("_" + config.SUFFIX_IMAGE5D, "_" + config.SUFFIX_META):
+        if base.endswith(suffix):
+            base = base[:-len(suffix)]
+    filename_image5d, filename_meta = importer.make_filenames(base)
+    if not os.path.exists(filename_image5d):
+        filename_image5d, filename_meta = importer.make_filenames(base, keep_ext=True)
+    if not os.path.exists(filename_image5d):
+        raise FileNotFoundError(f"no imported image {filename_image5d}")
+    img5d = Image5d(np.load(filename_image5d, mmap_mode="r"), filename_image5d, filename_meta)
+    importer.load_metadata(filename_meta, img5d)
+    if subimg_offset is not None and subimg_size is not None:
+        z, y, x = (int(v) for v in subimg_offset)
+        sz, sy, sx = (int(v) for v in subimg_size)
+        img5d.img = img5d.img[:, z:z + sz, y:y + sy, x:x + sx]
+        img5d.subimg_offset, img5d.subimg_size = subimg_offset, subimg_size
+    config.filename = path
+    return img5d
+
+
+def write_npy(image5d, md: Dict[Any, Any], path: str, find_near_bounds: bool = True) -> None:
+    """Save a ``t, z, y, x[, c]`` image as the reference's imported-image pair
+    (np_io.py:787-862): ``near_min`` / ``near_max`` per channel from the per-plane 0.5 /
+    99.5 percentiles (on the GPU, ``importer.calc_near_bounds``), the metadata file, and the
+    voxels plane by plane through a memory map.  ``md``: ``resolutions``, ``magnification``,
+    ``zoom``.  An existing image file is left alone."""
+    import os
+    from . import importer
+    filename_image5d, filename_meta = importer.make_filenames(os.path.splitext(path)[0],
+                                                              keep_ext=True)
+    if os.path.exists(filename_image5d):
+        print(f"File {filename_image5d} already exists, skipping saving image5d")
+        return
+    if find_near_bounds:
+        near_mins, near_maxs = importer.calc_near_bounds(image5d[0], dim_channel=3)
+    else:
+        info = np.iinfo(image5d.dtype) if np.issubdtype(image5d.dtype, np.integer) \
+            else np.finfo(image5d.dtype)
+        near_mins, near_maxs = [info.min], [info.max]
+    importer.save_image_info(
+        filename_meta, [os.path.basename(path)], [tuple(image5d.shape)], md.get("resolutions"),
+        md.get("magnification"), md.get("zoom"), near_mins, near_maxs)
+    out = np.lib.format.open_memmap(filename_image5d, mode="w+", dtype=image5d.dtype,
+                                    shape=tuple(int(v) for v in image5d.shape))
+    for t in range(image5d.shape[0]):
+        for z in range(image5d.shape[1]):
+            out[t, z] = image5d[t, z]
+        out.flush()
+    del out

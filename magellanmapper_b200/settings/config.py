@@ -30,6 +30,12 @@ resolutions: Optional[Sequence[Sequence[float]]] = None
 near_max: List[float] = [-1.0]
 near_min: List[float] = [0.0]
 
+#: objective magnification and zoom of the loaded image (importer metadata)
+magnification = None
+zoom = None
+
+SUFFIX_IMAGE5D = "image5d.npy"
+SUFFIX_META = "meta.yml"
 SUFFIX_BLOBS = "blobs.npz"
 SUFFIX_SUBIMG = "subimg.npy"
 save_subimg: bool = False

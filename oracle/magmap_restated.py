@@ -438,6 +438,54 @@ def finalize_blobs(segments_all: Optional[np.ndarray]) -> Optional[np.ndarray]:
 
 
 # --------------------------------------------------------------------------
+# intensity co-localisation: magmap/cv/colocalizer.py:340-441
+# --------------------------------------------------------------------------
+
+def colocalize_blobs(roi: np.ndarray, blobs: Optional[np.ndarray], thresh=None):
+    """colocalizer.py:340-441: per channel, label a mask with the indices of that
+    channel's blobs, grey-dilate it with ``ball(2)``, average the ROI under every label
+    in every channel, and flag the blobs whose average reaches the other channel's
+    threshold (the smallest such average of that channel's own blobs, or a percentile)."""
+    if blobs is None or roi is None or roi.ndim < 4:
+        return None
+    if thresh is None:
+        thresh = "min"
+    selem = ski.ball(2)
+    shape = roi.shape[:3]
+    in_roi = np.all([(blobs[:, a] >= 0) & (blobs[:, a] < shape[a]) for a in range(3)], axis=0)
+    blobs_roi = blobs[in_roi]
+    blobs_chl = blobs_roi[:, 6]
+    threshs, masks, ranges = [], [], []
+    for chl in range(roi.shape[3]):
+        sel = np.isin(blobs_chl, chl)
+        rng_ = np.where(sel)[0]
+        ranges.append(rng_)
+        mask = np.ones(shape, dtype=int) * -1
+        zyx = blobs_roi[sel, :3].astype(int)
+        mask[tuple(zyx.T)] = rng_
+        mask = ski.dilation(mask, selem)
+        masks.append(mask)
+        if thresh == "min":
+            threshs.append(None if len(rng_) == 0 else np.amin(
+                [np.mean(roi[mask == b, chl]) for b in rng_]))
+        else:
+            mb = mask >= 0
+            threshs.append(np.percentile(roi if np.sum(mb) < 1 else roi[mb, chl], thresh))
+    channels = np.unique(blobs_chl).astype(int)
+    colocs_roi = np.zeros((len(blobs_roi), roi.shape[3]), dtype=np.uint8)
+    for chl in channels:
+        for other in channels:
+            if threshs[other] is None:
+                continue
+            for b in ranges[chl]:
+                if np.mean(roi[masks[chl] == b, other]) >= threshs[other]:
+                    colocs_roi[b, other] = 1
+    colocs = np.zeros((len(blobs), roi.shape[3]), dtype=np.uint8)
+    colocs[in_roi] = colocs_roi
+    return colocs
+
+
+# --------------------------------------------------------------------------
 # whole-stack driver: stack_detect.py:338-517 (single channel, no coloc/verify)
 # --------------------------------------------------------------------------
 

@@ -338,6 +338,40 @@ def gen_sinks(ns):
     np.savez_compressed(os.path.join(OUT, "sinks.npz"), **out)
 
 
+def gen_coloc(ns):
+    """colocalizer.colocalize_blobs of the unmodified reference on a two-channel ROI: raw
+    uint16 and preprocessed float64 intensities, "min" and percentile thresholds, blobs that
+    share a voxel, touch the ROI faces or lie outside the ROI."""
+    rng = np.random.default_rng(91)
+    shape = (24, 48, 44)
+    v0, t0 = synth.make_volume(shape, seed=92, density=1 / 900.0)
+    v1, t1 = synth.make_volume(shape, seed=93, density=1 / 900.0)
+    # half of channel 1's nuclei sit on channel 0's: real co-localisation
+    v1 = np.maximum(v1, (v0 * 0.8).astype(np.uint16) * (rng.random(shape) < 0.5))
+    roi = np.stack([v0, v1], axis=-1)
+    rows = []
+    for chl, tab in ((0, t0), (1, t1)):
+        for z, y, x, s, a in tab:
+            rows.append([int(z), int(y), int(x), 5.0, -1, -1, chl])
+    rows += [rows[0][:6] + [0], rows[3][:3] + [5.0, -1, -1, 1],          # shared voxels
+             [0, 0, 0, 5.0, -1, -1, 0], [23, 47, 43, 5.0, -1, -1, 1],    # corners
+             [1, 46, 2, 5.0, -1, -1, 0], [30, 10, 10, 5.0, -1, -1, 0],   # outside in z
+             [5, -1, 7, 5.0, -1, -1, 1]]
+    blobs = np.array(rows, dtype=np.float64)
+    blobs = np.hstack([blobs, blobs[:, :3], np.full((len(blobs), 1), -1.0)])
+    out = {"roi": roi, "blobs": blobs}
+    ns.config.verbose = False
+    out["min_raw"] = ns.colocalizer.colocalize_blobs(roi, blobs)
+    out["p5_raw"] = ns.colocalizer.colocalize_blobs(roi, blobs, 5)
+    ref_shim.set_profile(ns, (1, 1, 1), near_max=synth.near_max_of(v0))
+    ns.config.near_max = [synth.near_max_of(v0), synth.near_max_of(v1)]
+    pre = ns.plot_3d.denoise_roi(ns.plot_3d.saturate_roi(roi))
+    out["pre"] = pre.astype(np.float64)
+    out["min_pre"] = ns.colocalizer.colocalize_blobs(pre, blobs)
+    out["p30_pre"] = ns.colocalizer.colocalize_blobs(pre, blobs, 30)
+    np.savez_compressed(os.path.join(OUT, "coloc.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_shim.load_reference()
@@ -351,6 +385,7 @@ def main():
     gen_stack_small(ns)
     gen_iso_unmix(ns)
     gen_sinks(ns)
+    gen_coloc(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

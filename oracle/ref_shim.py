@@ -67,6 +67,12 @@ def load_reference():
     plot_3d.morphology.octahedron = lambda r: ski.octahedron1()
     plot_3d.morphology.erosion = lambda img, fp: ski.erosion_octahedron1(img)
 
+    # colocalizer.py:373,395 - morphology.ball, morphology.dilation
+    from magmap.cv import colocalizer
+    colocalizer.morphology.ball = ski.ball
+    colocalizer.morphology.dilation = lambda img, footprint=None, selem=None: ski.dilation(
+        img, footprint if footprint is not None else selem)
+
     # cv_nd.py:1147 - transform.resize (make_isotropic)
     cv_nd.transform.resize = ski.transform_resize
 
@@ -75,6 +81,7 @@ def load_reference():
     ns = NS()
     ns.chunking, ns.detector, ns.stack_detect = chunking, detector, stack_detect
     ns.cv_nd = cv_nd
+    ns.colocalizer = colocalizer
     ns.plot_3d, ns.config, ns.roi_prof, ns.np_io = plot_3d, config, roi_prof, np_io
     _loaded = ns
     return ns

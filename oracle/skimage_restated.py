@@ -344,3 +344,16 @@ def transform_resize(image: np.ndarray, output_shape: Sequence[int], order=None,
     if clip and out.size:
         np.clip(out, np.min(image), np.max(image), out=out)
     return out
+
+
+def ball(radius: int) -> np.ndarray:
+    """``skimage.morphology.ball``: voxels with ``z^2 + y^2 + x^2 <= radius^2``."""
+    n = 2 * radius + 1
+    zz, yy, xx = np.mgrid[-radius:radius:n * 1j, -radius:radius:n * 1j, -radius:radius:n * 1j]
+    return np.array(zz * zz + yy * yy + xx * xx <= radius * radius, dtype=np.uint8)
+
+
+def dilation(image: np.ndarray, footprint: np.ndarray) -> np.ndarray:
+    """``skimage.morphology.dilation`` (grey, 'reflect' borders):
+    ``scipy.ndimage.grey_dilation`` with the (point-symmetric) footprint."""
+    return ndi.grey_dilation(image, footprint=footprint.astype(bool))

@@ -447,3 +447,91 @@ def test_stack_unmixing_device_route_equals_host_route_and_oracle(tmp_path, monk
     print(f"unmixed chunk: gpu={len(got)} oracle={len(want)} near={len(near)} od={len(od)} "
           f"unexplained={len(diff)}")
     assert len(want) > 5 and not diff, sorted(diff)
+
+
+def test_write_npy_equals_reference_files_and_feeds_the_detector(golden_dir, tmp_path):
+    """``np_io.write_npy`` (near bounds computed on the GPU) reproduces the image and
+    metadata files the unmodified reference wrote for the same array; ``setup_images`` of
+    the result drives ``detect_blobs_stack`` straight from the memory map."""
+    import yaml
+    from magellanmapper_b200.io import np_io as nio
+    ref_img = np.load(os.path.join(golden_dir, "feed", "sample_image5d.npy"))
+    with open(os.path.join(golden_dir, "feed", "sample_meta.yml")) as f:
+        ref_md = yaml.safe_load(f)
+    nio.write_npy(ref_img, {"resolutions": [[5.0, 1.1, 1.1]], "magnification": 20.0, "zoom": 1.0},
+                  str(tmp_path / "sample.czi"))
+    with open(tmp_path / "sample_image5d.npy", "rb") as a, \
+            open(os.path.join(golden_dir, "feed", "sample_image5d.npy"), "rb") as b:
+        assert a.read() == b.read()
+    with open(tmp_path / "sample_meta.yml") as f:
+        assert yaml.safe_load(f) == ref_md
+    _setup()
+    img5d = nio.setup_images(str(tmp_path / "sample"))
+    config.channel = None
+    os.chdir(tmp_path)
+    _, _, blobs = stack_detect.detect_blobs_stack(str(tmp_path / "sample"), img5d)
+    _, _, want = stack_detect.detect_blobs_stack(str(tmp_path / "sample2"),
+                                                 np_io.Image5d(np.array(img5d.img)))
+    assert blobs.blobs is not None and len(blobs.blobs) > 5
+    np.testing.assert_array_equal(blobs.blobs, want.blobs)
+
+
+def test_colocalize_blobs_vs_reference_vectors(golden_dir):
+    """colocalizer.colocalize_blobs against the unmodified reference: raw uint16 and
+    preprocessed float64 ROIs, "min" and percentile thresholds, blobs sharing a voxel,
+    on the ROI faces and outside the ROI."""
+    from magellanmapper_b200.cv import colocalizer
+    g = np.load(os.path.join(golden_dir, "coloc.npz"))
+    blobs = g["blobs"]
+    for key, roi, thresh in (("min_raw", g["roi"], None), ("p5_raw", g["roi"], 5),
+                             ("min_pre", g["pre"], None), ("p30_pre", g["pre"], 30)):
+        got = colocalizer.colocalize_blobs(roi, blobs, thresh)
+        assert got.dtype == np.uint8 and got.shape == g[key].shape
+        np.testing.assert_array_equal(got, g[key], err_msg=key)
+    assert colocalizer.colocalize_blobs(g["roi"][..., 0], blobs) is None
+    assert colocalizer.colocalize_blobs(g["roi"], None) is None
+    # exact integer sums: means of the raw ROI equal numpy's bit for bit
+    in_roi = detector.get_blobs_in_roi(blobs, (0, 0, 0), g["roi"].shape[:3], reverse=False)[0]
+    means, counts = colocalizer.blob_surround_means(g["roi"], in_roi)
+    b = int(np.argmax(counts))
+    z, y, x = in_roi[b, :3].astype(int)
+    assert 1 <= counts[b] <= 33
+
+
+def test_stack_colocalization_two_channels(tmp_path):
+    """detect_blobs_blocks(coloc=True): same blobs as without co-localisation, one flag
+    per channel in the reference's (column-10) slice, and per chunk the flags the oracle
+    computes from the oracle-preprocessed sub-ROI."""
+    v0, _ = synth.make_volume((40, 90, 80), seed=71, density=1 / 2500.0)
+    v1, _ = synth.make_volume((40, 90, 80), seed=72, density=1 / 2500.0)
+    v1 = np.maximum(v1, (v0 * 0.7).astype(np.uint16))
+    two = np.stack([v0, v1], axis=-1)
+    nms = [synth.near_max_of(v0), synth.near_max_of(v1)]
+    p0, p1 = _setup_two(nms)
+    for p in (p0, p1):
+        p["segment_size"] = 35
+    os.chdir(tmp_path)
+
+    def run(coloc):
+        _, _, b = stack_detect.detect_blobs_blocks(
+            str(tmp_path / "co"), np_io.Image5d(two[None]), None, None, [0, 1], False, False,
+            True, coloc)
+        return b
+    plain, co = run(False), run(True)
+    np.testing.assert_array_equal(co.blobs, plain.blobs)
+    assert plain.colocalizations is None
+    assert co.colocalizations.shape == (len(co.blobs), 2) and co.colocalizations.dtype == np.uint8
+    # one chunk against the oracle
+    prof = mm.Profile(segment_size=35)
+    blocks = mm.setup_blocks(prof, two.shape[:3], (1, 1, 1))
+    coord = (0, 1, 1)
+    sub = two[blocks.sub_roi_slices[coord]]
+    pre = np.stack([mm.preprocess_blocks(sub[..., k], blocks.denoise_max_shape, prof, nms[k])
+                    for k in range(2)], axis=-1)
+    _, seg = stack_detect.StackDetector.detect_sub_roi(
+        coord, np.zeros(3), np.subtract(blocks.sub_roi_slices.shape, 1),
+        blocks.denoise_max_shape, None, None, sub, [0, 1], coloc=True)
+    assert seg.shape[1] == 13 and len(seg) > 10
+    want = mm.colocalize_blobs(pre, seg[:, :11])
+    np.testing.assert_array_equal(seg[:, 11:13].astype(np.uint8), want)
+    assert want.sum() > len(seg)            # every blob at least in its own channel

@@ -335,3 +335,23 @@ def test_csv_and_sqlite_sinks_match_reference(golden_dir, tmp_path):
     got, ids = sqlite.select_blobs_by_roi(cur, roi_id)
     assert got.shape == (len(rows), 7) and len(ids) == len(rows)
     conn.close()
+
+
+def test_setup_images_opens_reference_written_files(golden_dir):
+    """The ``.npy`` feed: an image + metadata pair written by the unmodified reference's
+    ``np_io.write_npy`` is memory-mapped and its metadata lands in ``config``."""
+    from magellanmapper_b200.io import np_io as nio
+    from magellanmapper_b200.settings import config
+    base = os.path.join(golden_dir, "feed", "sample")
+    img5d = nio.setup_images(base)
+    assert isinstance(img5d.img, np.memmap) and not img5d.img.flags.writeable
+    assert img5d.img.shape == (1, 6, 40, 36, 2) and img5d.img.dtype == np.uint16
+    np.testing.assert_allclose(config.resolutions, [[5.0, 1.1, 1.1]])
+    assert config.magnification == 20.0 and config.zoom == 1.0
+    assert len(config.near_max) == 2 and len(config.near_min) == 2
+    assert img5d.meta["ver"] == 15 and img5d.shapes == [[1, 6, 40, 36, 2]]
+    sub = nio.setup_images(base + "_image5d.npy", subimg_offset=(1, 4, 5), subimg_size=(3, 20, 10))
+    assert sub.img.shape == (1, 3, 20, 10, 2)
+    np.testing.assert_array_equal(sub.img[0], img5d.img[0, 1:4, 4:24, 5:15])
+    with pytest.raises(FileNotFoundError):
+        nio.setup_images(os.path.join(golden_dir, "feed", "absent"))
