@@ -424,7 +424,9 @@ int preprocess_impl(const void* in, int dtype, const int64_t st[3], int Z, int Y
                     int by, int bx, const mmb_preproc_params* p, float* out, int64_t pitch,
                     cudaStream_t s, void* scratch, int64_t scratch_bytes) {
   bz = bz < Z ? bz : Z; by = by < Y ? by : Y; bx = bx < X ? bx : X;
-  if (bz > 32 || by > 32 || bx > 32) {
+  // float64 input: the shared-memory kernel holds the block as float32, which would take the
+  // percentiles of ROUNDED samples; the global-memory path selects on the float64 keys
+  if (bz > 32 || by > 32 || bx > 32 || dtype == MMB_F64) {
     // blocks that do not fit one CTA's shared memory: global-memory path
     if (scratch_bytes < preprocess_large_work_bytes(Z, Y, pitch, bz, by, bx)) scratch = nullptr;
     return preprocess_large_impl(in, dtype, st, Z, Y, X, bz, by, bx, p, out, pitch, scratch, s);

@@ -383,6 +383,7 @@ def test_preprocess_anisotropic_blocks(gpu):
     ((20, 66, 41), (25, 33, 64), np.uint8),       # mixed: z and x clipped to the volume
     ((34, 40, 40), (34, 40, 40), np.float32),     # one block, float keys
     ((12, 70, 35), (2000, 2000, 2000), np.float64),   # `lowres`: block = chunk
+    ((30, 50, 26), (25, 25, 25), np.float64),         # float64 keys at the default block size
 ])
 def test_preprocess_large_blocks(gpu, shape, block, dtype):
     """Blocks above 32 voxels a side (global-memory path, preprocess_large.cu): radix-select
