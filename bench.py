@@ -215,12 +215,12 @@ def roofline_block(ms, cnt, units):
 # CPU baseline (oracle = the reference algorithm restated on scipy)
 # ----------------------------------------------------------------------------
 
-def cpu_sample_shape(cores, shape):
+def cpu_sample_shape(cores, shape, seconds=20.0):
     """The first P planes of the stack (up to 2048 x 2048 of each), P sized for about
-    20 s of CPU work at ~0.7 MVoxel/s/core (measured on the GPU box's host).  The reference's own chunking
+    ``seconds`` (20) s of CPU work at ~0.7 MVoxel/s/core (measured on the GPU box's host).  The reference's own chunking
     (segment_size 500, overlap 5) then cuts it into up to 25 chunks of P x 505 x 505."""
     y, x = min(shape[1], 2048), min(shape[2], 2048)
-    target = 0.7e6 * cores * 20.0
+    target = 0.7e6 * cores * seconds
     p = int(max(16, min(shape[0], round(target / (y * x)))))
     return (p, y, x)
 
@@ -692,6 +692,8 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for k in gpu.STATS:
+        gpu.STATS[k] = 0
     launches0 = lib.mmb_launch_count()
     lib.mmb_profile_enable(1)
     barrier()
@@ -709,6 +711,8 @@ def main():
     n_blobs = 0 if final is None else len(final)
     stage_times = None if res is None or not getattr(res, "times", None) else {
         k.value: round(float(v[0]), 4) for k, v in res.times.items()}
+    if world > 1 and multi_gpu.LAST_STAGE_S:
+        stage_times = {k: round(v, 4) for k, v in multi_gpu.LAST_STAGE_S.items()}
     ms, cnt, units = collect_profile(lib)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -824,7 +828,13 @@ def main():
         "config": {"workload": workload,
                    "l2": "inputs larger than L2 (every sweep streams >= 1 GB per launch)",
                    "blobs_per_step": n_blobs, "host_stage_s_last_step": stage_times,
-                   "multi_gpu": multi, "parity": parity},
+                   "multi_gpu": multi, "parity": parity,
+                   "prune_within_chunks_rank0_per_step": {
+                       k: v // max(args.steps, 1) for k, v in gpu.STATS.items()},
+                   "prune_note": "order_dependent = local maxima whose survival in scikit-image's "
+                                 "_prune_blobs depends on the iteration order of its pair set "
+                                 "(kill chains); the GPU resolves them order-independently "
+                                 "(DESIGN.md section 4)"},
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
         "clocks": clocks,
     }
@@ -840,7 +850,8 @@ def run_reference(args, rank, world, shape, cores):
     if rank != 0:
         return
     from magellanmapper_b200 import synth
-    sshape = cpu_sample_shape(cores, shape)
+    # many steps of this arm run back to back: about 8 s of CPU work each
+    sshape = cpu_sample_shape(cores, shape, seconds=8.0)
     sample, _ = synth.make_volume(sshape, SEED)
     near_max = synth.near_max_of(sample)
     for _ in range(min(args.warmup, 1)):

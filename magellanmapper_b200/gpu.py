@@ -347,6 +347,12 @@ def prune_seams(master_zyx: torch.Tensor, check_zyx: torch.Tensor, tol: Sequence
     return master_last[:nm], check_hit[:nc]
 
 
+#: running totals over every chunk collected in this process (``bench.py`` reports them):
+#: local maxima, survivors of the overlap pruning, and the size of the set whose survival
+#: in scikit-image depends on its pair iteration order
+STATS = {"peaks": 0, "survivors": 0, "order_dependent": 0}
+
+
 class _Slot:
     """Output buffers of one in-flight chunk: device candidates and status, and
     their pinned host mirrors."""
@@ -440,7 +446,7 @@ class ChunkDetector:
         buffers (counted exactly on the device) is redone once with larger ones."""
         slot = ticket.slot
         ticket.event.synchronize()
-        n_peaks, n_out, n_edges, _ = (int(v) for v in slot.status_host)
+        n_peaks, n_out, n_edges, n_od = (int(v) for v in slot.status_host)
         edge_cap = self.lib.mmb_detect_edge_capacity(slot.capacity)
         if n_peaks > slot.capacity or n_edges > edge_cap:
             slot.busy = False
@@ -448,6 +454,9 @@ class ChunkDetector:
             self.capacity = max(self.capacity, int(need * 1.25) + 1024)
             self._alloc()
             return self.detect(*ticket.args)
+        STATS["peaks"] += n_peaks
+        STATS["survivors"] += n_out
+        STATS["order_dependent"] += n_od
         if n_out == 0:
             slot.busy = False
             return np.zeros(0, dtype=CAND_DTYPE), n_peaks
@@ -465,7 +474,7 @@ class ChunkDetector:
         three status counters cross to the host."""
         slot = ticket.slot
         ticket.event.synchronize()
-        n_peaks, n_out, n_edges, _ = (int(v) for v in slot.status_host)
+        n_peaks, n_out, n_edges, n_od = (int(v) for v in slot.status_host)
         edge_cap = self.lib.mmb_detect_edge_capacity(slot.capacity)
         if n_peaks > slot.capacity or n_edges > edge_cap:
             slot.busy = False
@@ -475,6 +484,9 @@ class ChunkDetector:
             with torch.cuda.stream(ticket.stream or torch.cuda.current_stream()):
                 redo = self.enqueue(*ticket.args)
             return self.collect_device(redo)
+        STATS["peaks"] += n_peaks
+        STATS["survivors"] += n_out
+        STATS["order_dependent"] += n_od
         # copy on the stream the chunk ran on: the slot may then be reused by a later
         # chunk of that stream right away (consumers on another stream must order
         # themselves after it)

@@ -406,6 +406,23 @@ def box_transfer_plan(loans, z_bounds, y_bounds, held):
     return plan
 
 
+#: stage times of the last ``detect_blobs_blocks_slabs`` call of this rank, in seconds, when
+#: the environment sets MMB_STAGE_SYNC (every stage then ends with a device synchronisation,
+#: which the normal path avoids): plane exchange, box exchange, detection, gather, tables
+LAST_STAGE_S: Dict[str, float] = {}
+
+
+def _stage(name: str, t0: float) -> float:
+    import os
+    import time
+    if os.environ.get("MMB_STAGE_SYNC"):
+        torch.cuda.synchronize()
+        now = time.perf_counter()
+        LAST_STAGE_S[name] = LAST_STAGE_S.get(name, 0.0) + now - t0
+        return now
+    return t0
+
+
 def detect_blobs_blocks_slabs(filename_base: str, slab, held: Sequence[Range],
                               global_shape: Sequence[int],
                               channels: Optional[Sequence[int]] = None, group=None,
@@ -446,6 +463,9 @@ def detect_blobs_blocks_slabs(filename_base: str, slab, held: Sequence[Range],
                     and settings["isotropic"] is None)
     streamed = host_slab and slab.flags.c_contiguous and device_route
     prefix = suffix = None
+    import time as _time
+    LAST_STAGE_S.clear()
+    _t = _time.perf_counter()
     if streamed:
         # the slab stays on the host and is streamed strip by strip under the kernels;
         # only the halo planes of the neighbours are exchanged up front
@@ -477,7 +497,9 @@ def detect_blobs_blocks_slabs(filename_base: str, slab, held: Sequence[Range],
         # prunes the seams on its GPU
         from .cv import device_tables
         dev = torch.device("cuda", torch.cuda.current_device()) if host_slab else slab.device
+        _t = _stage("exchange_planes", _t)
         boxes = _exchange_boxes(slab, held, loans, z_bounds, y_bounds, group, dev)
+        _t = _stage("exchange_boxes", _t)
         tables = device_tables.ChunkTables(dev, channels)
         if coords:
             stack_detect.StackDetector.detect_blobs_sub_rois_device(
@@ -498,8 +520,10 @@ def detect_blobs_blocks_slabs(filename_base: str, slab, held: Sequence[Range],
                 coords=unit, tables=tables)
         # 32-byte rows travel; rank 0 orders them by chunk (whoever worked on it), prunes
         # the seams and formats the table with the library's table kernels
+        _t = _stage("detect", _t)
         parts = gather_tensor_rows(tables.rows(), device_tables.ROW_INTS, group,
                                    dtype=torch.int32, device=dev)
+        _t = _stage("gather", _t)
         if rank != 0:
             return None, None, None
         allr = parts[0] if len(parts) == 1 else torch.cat(parts)
@@ -507,6 +531,7 @@ def detect_blobs_blocks_slabs(filename_base: str, slab, held: Sequence[Range],
             allr, stack_detect.channel_ladders(slab, blocks.denoise_max_shape, channels),
             blocks.overlap, blocks.tol, blocks.sub_roi_slices, channels,
             blocks.overlap_padding, final_layout=True)
+        _t = _stage("tables", _t)
         final_on_device = True
     else:
         seg_rois = None
