@@ -350,6 +350,27 @@ def skimage_ladder(lo, hi, num_sigma: int) -> np.ndarray:
     return (scale * (hi - lo) + lo).astype(np.float64)
 
 
+def img_as_float_host(arr: np.ndarray) -> np.ndarray:
+    """``skimage.util.img_as_float`` on the host for the dtypes the kernels do not read in
+    place (bool, signed and 32/64-bit integers, float16): bool -> 0 / 1, unsigned ->
+    ``x / max``, signed -> ``(2 x + 1) / (max - min)``, all in float64."""
+    dt = arr.dtype
+    if dt.kind == "f":
+        return arr.astype(np.float32 if dt == np.float16 else dt)
+    if dt.kind == "b":
+        return arr.astype(np.float64)
+    if dt.kind == "u":
+        return arr.astype(np.float64) / float(np.iinfo(dt).max)
+    if dt.kind == "i":
+        info = np.iinfo(dt)
+        out = arr.astype(np.float64)
+        out *= 2.0
+        out += 1.0
+        out /= float(info.max) - float(info.min)
+        return out
+    raise TypeError(f"unsupported image dtype {dt}")
+
+
 def input_scale(dtype) -> float:
     """``skimage.util.img_as_float`` factor for an input dtype."""
     dtype = np.dtype(dtype)
@@ -440,6 +461,10 @@ def enqueue_detection(det, roi, channels: Sequence[int], multichannel: bool,
     block = tuple(int(v) for v in denoise_max_shape) if denoise_max_shape is not None \
         else (1, 1, 1)
     tickets = []
+    if (isinstance(roi, np.ndarray) and denoise_max_shape is None and isotropic is None
+            and roi.dtype not in (np.uint8, np.uint16, np.float32, np.float64)):
+        # dtypes the kernels do not read in place: scikit-image's own conversion, on the host
+        roi = img_as_float_host(roi)
     if isotropic is None and not any(unmix.values()):
         for chl in channels:
             settings = config.get_roi_profile(chl)

@@ -648,7 +648,7 @@ def seamless_plan(n_planes: int, world: int, block_depth: int, halo_planes: int)
     return own, ext
 
 
-def _seamless_setup(global_shape, channel):
+def _seamless_setup(global_shape, channel, image_is_f32: bool = False):
     from .cv import detector, stack_detect
     from .plot import plot_3d
     from .settings import config
@@ -658,7 +658,9 @@ def _seamless_setup(global_shape, channel):
     scale = detector.calc_scaling_factor()[2]
     dms = blocks.denoise_max_shape
     pre = plot_3d.preproc_params(settings, channel) if dms is not None else None
-    sigmas = detector.sigma_ladder(settings, scale, False)
+    # a raw float32 image gets scikit-image's float32-rounded ladder; preprocessing yields
+    # float64 in the reference
+    sigmas = detector.sigma_ladder(settings, scale, image_is_f32 and dms is None)
     halo = int(4.0 * float(np.max(sigmas)) + 0.5) + 1          # r_max + 1
     bd = (int(dms[0]), int(dms[1]), int(dms[2])) if dms is not None else (1, 1, 1)
     return settings, pre, sigmas, halo, bd
@@ -679,7 +681,8 @@ def seamless_candidates(ext, ext_range: Range, own_range: Range, global_shape: S
     from collections import deque
     from . import gpu, _lib
     lib = _lib.load()
-    settings, pre, sigmas, halo, bd = _seamless_setup(global_shape, channel)
+    settings, pre, sigmas, halo, bd = _seamless_setup(global_shape, channel,
+                                                      ext.dtype == torch.float32)
     Z, Y, X = (int(v) for v in global_shape[:3])
     e0, e1 = ext_range
     z0, z1 = own_range
@@ -773,7 +776,8 @@ def detect_seamless(slab, held: Sequence[Range], global_shape: Sequence[int],
     ``peak_local_max`` order (None if empty), None elsewhere.
     """
     rank, world = _world(group)
-    settings, pre, sigmas, halo, bd = _seamless_setup(global_shape, channel)
+    settings, pre, sigmas, halo, bd = _seamless_setup(global_shape, channel,
+                                                      slab.dtype == torch.float32)
     Z, Y, X = (int(v) for v in global_shape[:3])
     own, ext_ranges = seamless_plan(Z, world, bd[0], halo)
     # the caller's slabs need not coincide with the block-aligned owned slabs

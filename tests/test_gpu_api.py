@@ -535,3 +535,18 @@ def test_stack_colocalization_two_channels(tmp_path):
     want = mm.colocalize_blobs(pre, seg[:, :11])
     np.testing.assert_array_equal(seg[:, 11:13].astype(np.uint8), want)
     assert want.sum() > len(seg)            # every blob at least in its own channel
+
+
+def test_detect_blobs_other_integer_dtypes_follow_img_as_float():
+    """int16 / uint32 / int32 ROIs are converted as scikit-image's ``img_as_float`` does
+    (signed: ``(2 x + 1) / (max - min)``), not read as raw counts."""
+    vol, _ = synth.make_volume((24, 70, 64), seed=33, density=1 / 1500.0)
+    _setup()
+    for dt, conv in ((np.int16, lambda v: (v // 2).astype(np.int16)),
+                     (np.uint32, lambda v: v.astype(np.uint32) * 65537),
+                     (np.int32, lambda v: (v.astype(np.int64) * 32768).astype(np.int32))):
+        roi = conv(vol)
+        want = mm.detect_blobs(roi, mm.Profile(), (1, 1, 1), 0)
+        got = detector.detect_blobs(roi, [0])
+        assert want is not None and len(want) > 10
+        assert len(set(_rows(got)) ^ set(_rows(want))) <= max(1, len(want) // 200), dt
