@@ -155,20 +155,7 @@ conv_x_tma_kernel(const __grid_constant__ CUtensorMap tm_in,
       // (A, B) of one output share an FFMA2: the pair (g, h) is a 64-bit uniform
       // operand, the input value the broadcast scalar
       float2 acc[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int i = G::R4 - R; i < G::R4 + 16 + R; ++i) {
-        const float2 vv = make_float2(win[i], win[i]);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int t = i - (G::R4 + j);
-          if (t >= -R && t <= R) {
-            const int wi = t < 0 ? -t : t;
-            acc[j] = ffma2(vv, w.gh[wi], acc[j]);
-          }
-        }
-      }
+      x_taps_sym<R, G::R4, G::W>(win, acc, w);
       unsigned char* oa = s_a + lane * 128;
       unsigned char* ob = s_b + lane * 128;
 #pragma unroll
@@ -343,17 +330,7 @@ conv_x_ws_kernel(const __grid_constant__ CUtensorMap tm_in,
       if (lane == 0) mbar_arrive(&empty_in[s]);         // the slot may be refilled
 
       float2 acc[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int i = G::R4 - R; i < G::R4 + 16 + R; ++i) {
-        const float2 vv = make_float2(win[i], win[i]);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int tt = i - (G::R4 + j);
-          if (tt >= -R && tt <= R) acc[j] = ffma2(vv, w.gh[tt < 0 ? -tt : tt], acc[j]);
-        }
-      }
+      x_taps_sym<R, G::R4, G::W>(win, acc, w);
 
 #ifdef MMB_WS_DIRECT
       {
@@ -539,17 +516,7 @@ conv_x_warp_kernel(const float* __restrict__ in, float* __restrict__ outA,
         win[4 * c + 0] = v.x; win[4 * c + 1] = v.y; win[4 * c + 2] = v.z; win[4 * c + 3] = v.w;
       }
       float2 acc[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int i = G::R4 - R; i < G::R4 + 16 + R; ++i) {
-        const float2 vv = make_float2(win[i], win[i]);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int tt = i - (G::R4 + j);
-          if (tt >= -R && tt <= R) acc[j] = ffma2(vv, w.gh[tt < 0 ? -tt : tt], acc[j]);
-        }
-      }
+      x_taps_sym<R, G::R4, G::W>(win, acc, w);
       // A then B through the staging tile: lane = row writes, row-segment reads
 #pragma unroll
       for (int ab = 0; ab < 2; ++ab) {

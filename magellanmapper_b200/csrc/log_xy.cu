@@ -211,20 +211,7 @@ conv_xy_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __r
     const int row = org + lane;
     if (x_active && row >= row_first) {
       float2 acc[16];
-#pragma unroll
-      for (int jj = 0; jj < 16; ++jj) acc[jj] = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int i = R4 - R; i < R4 + 16 + R; ++i) {
-        const float2 vv = make_float2(win[i], win[i]);
-#pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
-          const int t = i - (R4 + jj);
-          if (t >= -R && t <= R) {
-            const int wi = t < 0 ? -t : t;
-            acc[jj] = ffma2(vv, w.gh[wi], acc[jj]);
-          }
-        }
-      }
+      x_taps_sym<R, R4, G::W>(win, acc, w);
       const int slot = (row - row_first) % RR;
       unsigned char* ra = ringA + slot * kFRowB;
       const int skey = slot & 7;
@@ -341,11 +328,10 @@ static int run_xy(const float* in, float* outC, float* outD, int Z, int Y, int X
 int launch_xy_fused(int r, const float* in, float* outC, float* outD, int Z, int Y, int X,
                     int64_t pitch, const LogWeights& w, cudaStream_t st) {
   const uintptr_t bits = (uintptr_t)in | (uintptr_t)outC | (uintptr_t)outD;
-  // measured on a 505^3 chunk (profiles/r02_kbench.jsonl): fused vs x + y sweeps 0.63 vs
-  // 0.71 ms at r = 12, 0.80 vs 0.84 at r = 16, 1.02 vs 0.99 at r = 20 - the saving of the A, B
-  // round trip shrinks as the arithmetic grows, and the longer prologue (two x tiles above
-  // r = 16) turns it into a loss around r = 19
-  static const int r_max = getenv("MMB_XY_RMAX") ? atoi(getenv("MMB_XY_RMAX")) : 18;
+  // measured on a 505^3 chunk (profiles/r02_kbench.jsonl), fused vs x + y sweeps: 0.58 vs 0.71 ms
+  // at r = 12, 0.74 vs 0.82 at r = 16, 0.93 vs 1.06 at r = 20.  MMB_XY_RMAX lowers the limit
+  // for A/B runs.
+  static const int r_max = getenv("MMB_XY_RMAX") ? atoi(getenv("MMB_XY_RMAX")) : 20;
   if (r > r_max || r > 20 || (bits & 15) != 0 || pitch % 4 != 0 || X < 32 || Y < 64 || Z > 65535)
     return MMB_ERR_UNSUPPORTED;
 #define XY_(RR) if (r <= RR) return run_xy<RR>(in, outC, outD, Z, Y, X, pitch, w, st);
