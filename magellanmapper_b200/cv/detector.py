@@ -585,8 +585,11 @@ def sort_blobs(blobs: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
 
 
 def _find_close_blobs(blobs: np.ndarray, blobs_master: np.ndarray, tol):
-    """Indices ``(close_master, close)`` of every (master, check) pair within
-    ``tol`` on all three axes, in master-major order - computed on the GPU."""
+    """The box match of ``remove_close_blobs`` on the GPU (``mmb_prune_seams``), in the form
+    the caller needs instead of the reference's pair lists (detector.py:1000-1006):
+    ``(last, hit)`` - for every master the index of the LAST check blob within ``tol`` on
+    all three axes in the reference's (tile, row) order, or -1; for every check blob
+    whether any master matched it."""
     import torch
     from .. import gpu
     dev = gpu.require_cuda()

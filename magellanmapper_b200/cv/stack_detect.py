@@ -34,8 +34,9 @@ _logger = config.logger.getChild(__name__)
 DEVICE_TABLES = True
 
 
-#: Chunks with at most this fraction of the largest chunk's voxels run on a side stream
-#: under the kernels of the full chunks (0 = off, the default).  Measured on config 2
+#: EXPERIMENTAL, off, and not used by any reported result: chunks with at most this fraction
+#: of the largest chunk's voxels run on a side stream under the kernels of the full chunks
+#: (0 = off, the default).  Measured on config 2
 #: with 0.3: 329 -> 319 ms per stack.  OFF because with a device-resident image the two
 #: streams run unsynchronised for a whole stack and the tables of a few thin chunks then
 #: vary from run to run (a handful of rows, occasionally the row count:
