@@ -24,7 +24,7 @@ int mmb_synth_nuclei(uint16_t* out, int Z, int Y, int X, int64_t z_off, int64_t 
 
 /* The fused x -> y sweep of mmb_log_scale on its own (csrc/log_xy.cu): C = g_y*(g_x*in),
  * D = h_y*(g_x*in) + g_y*(h_x*in).  MMB_ERR_UNSUPPORTED for the shapes and radii that
- * mmb_log_scale serves with the two separate sweeps (radius > 20, Y < 64, X < 32).     */
+ * mmb_log_scale serves with the two separate sweeps (radius > 20, Y < 32, X < 32).     */
 int mmb_log_xy_fused(const float* in, float* outC, float* outD, int Z, int Y, int X,
                      int64_t pitch, double sigma, void* stream);
 

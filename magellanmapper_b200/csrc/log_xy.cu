@@ -310,8 +310,10 @@ static int run_xy(const float* in, float* outC, float* outD, int Z, int Y, int X
   const int64_t want = (512 / kFThreads) * (int64_t)num_sms();
   int nseg = 1;
   if (ctas < want) {
-    nseg = (int)cdiv(want, ctas);
-    const int max_seg = (int)cdiv(Y, 4 * kFRows);
+    // as many segments as still fit ONE wave (a second, partly filled wave costs a whole
+    // march), of at least two steps each: a segment pays one or two prologue tiles
+    nseg = (int)(want / ctas);
+    const int max_seg = (int)cdiv(Y, 2 * kFRows);
     if (nseg > max_seg) nseg = max_seg;
     if (nseg < 1) nseg = 1;
   }
@@ -322,8 +324,8 @@ static int run_xy(const float* in, float* outC, float* outD, int Z, int Y, int X
   return MMB_OK;
 }
 
-// the fused sweep serves radii up to 20 on volumes whose rows are 16-byte aligned and whose
-// y extent leaves the 'reflect' sources inside the ring; everything else takes the two
+// the fused sweep serves radii up to 20 on volumes whose rows are 16-byte aligned and at least
+// 32 voxels long in x and y (the 'reflect' sources of every ring row then lie inside the ring); everything else takes the two
 // separate sweeps.  Returns MMB_ERR_UNSUPPORTED when the caller should do that.
 int launch_xy_fused(int r, const float* in, float* outC, float* outD, int Z, int Y, int X,
                     int64_t pitch, const LogWeights& w, cudaStream_t st) {
@@ -332,7 +334,7 @@ int launch_xy_fused(int r, const float* in, float* outC, float* outD, int Z, int
   // at r = 12, 0.74 vs 0.82 at r = 16, 0.93 vs 1.06 at r = 20.  MMB_XY_RMAX lowers the limit
   // for A/B runs.
   static const int r_max = getenv("MMB_XY_RMAX") ? atoi(getenv("MMB_XY_RMAX")) : 20;
-  if (r > r_max || r > 20 || (bits & 15) != 0 || pitch % 4 != 0 || X < 32 || Y < 64 || Z > 65535)
+  if (r > r_max || r > 20 || (bits & 15) != 0 || pitch % 4 != 0 || X < 32 || Y < 32 || Z > 65535)
     return MMB_ERR_UNSUPPORTED;
 #define XY_(RR) if (r <= RR) return run_xy<RR>(in, outC, outD, Z, Y, X, pitch, w, st);
   MMB_XY_BUCKETS(XY_)

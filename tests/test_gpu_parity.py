@@ -155,10 +155,11 @@ def test_log_scale_matches_scipy(gpu, shape, seed):
 
 
 @pytest.mark.parametrize("shape", [(9, 70, 140), (3, 64, 33), (5, 505, 505), (12, 200, 48),
-                                   (2, 97, 300), (40, 66, 129)])
+                                   (2, 97, 300), (40, 66, 129), (7, 48, 505), (3, 33, 70),
+                                   (4, 32, 32)])
 @pytest.mark.parametrize("sigma", [1.9, 3.0, 4.0, 4.4, 4.6, 5.0])
 def test_fused_xy_sweep_equals_separate_sweeps(gpu, shape, sigma):
-    """The fused x -> y sweep (log_xy.cu; radii <= 20, y extent >= 64) inside
+    """The fused x -> y sweep (log_xy.cu; radii <= 20, x and y extent >= 32) inside
     ``mmb_log_scale`` against the three separate sweeps of ``mmb_log_pass``: same
     accumulation order per output, so the LoG volumes are equal BIT FOR BIT; and against
     scipy within 1e-4.  Shapes cover ragged last tiles in x and y, pitch > X padding, planes
