@@ -13,6 +13,40 @@ constexpr int kCols = 128;
 constexpr int kMarchCols = MMB_MARCH_COLS;     // columns per CTA of the marching kernel
 constexpr int kTileThreads = 256;
 
+// marching kernel: ring of 2*RP + 2*STEP rows of both inputs, 512 threads per SM
+template <int R, int G>
+static int march(const float* in0, const float* in1, float* out0, float* out1, int n_axis,
+                 int64_t inner, int64_t outer, const LogWeights& w, float scale,
+                 cudaStream_t st) {
+  constexpr int NBM = MMB_MARCH_NB;
+  constexpr size_t smem = (size_t)2 * (2 * ((R + 7) / 8 * 8) + 2 * NBM * G) * kMarchCols * sizeof(float);
+  auto kern = conv_march_kernel<R, 2, NBM, G, kMarchCols>;
+  static bool configured = false;
+  if (!configured) {
+    MMB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+    configured = true;
+  }
+  // split the marched axis when columns x outer slices alone cannot fill the GPU
+  // (thin chunks, small ROIs): segments of a multiple of STEP rows, >= 4 steps each
+  constexpr int STEP = NBM * G;
+  const int64_t ctas = cdiv(inner, kMarchCols) * outer;
+  const int64_t want = (512 / (G * kMarchCols / 2)) * (int64_t)num_sms();
+  int nseg = 1;
+  if (ctas < want) {
+    nseg = (int)cdiv(want, ctas);
+    const int max_seg = (int)cdiv(n_axis, 4 * STEP);
+    if (nseg > max_seg) nseg = max_seg;
+    if (nseg < 1) nseg = 1;
+  }
+  const int seg_len = (int)cdiv(cdiv(n_axis, nseg), STEP) * STEP;
+  dim3 grid((unsigned)cdiv(inner, kMarchCols), (unsigned)cdiv(n_axis, seg_len), (unsigned)outer);
+  kern<<<grid, G * kMarchCols / 2, smem, st>>>(in0, in1, out0, out1, n_axis, inner,
+                                               (int64_t)n_axis * inner, w, scale, seg_len);
+  MMB_CHECK_LAUNCH();
+  return MMB_OK;
+}
+
 template <int R>
 static int run(const float* in0, const float* in1, float* out0, float* out1, int n_axis,
                int64_t inner, int64_t outer, const LogWeights& w, float scale,
@@ -23,34 +57,11 @@ static int run(const float* in0, const float* in1, float* out0, float* out1, int
   const bool aligned = (bits & 15) == 0 && inner % 4 == 0;
   if constexpr (R <= 20) {
     if (aligned) {
-      // marching kernel: ring of 2*RP + 2*STEP rows of both inputs, 2 CTAs per SM
-      constexpr int G = MMB_MARCH_G, NBM = MMB_MARCH_NB;
-      constexpr size_t smem = (size_t)2 * (2 * ((R + 7) / 8 * 8) + 2 * NBM * G) * kMarchCols * sizeof(float);
-      auto kern = conv_march_kernel<R, 2, NBM, G, kMarchCols>;
-      static bool configured = false;
-      if (!configured) {
-        MMB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)smem));
-        configured = true;
-      }
-      // split the marched axis when columns x outer slices alone cannot fill the GPU
-      // (thin chunks, small ROIs): segments of a multiple of STEP rows, >= 4 steps each
-      constexpr int STEP = NBM * G;
-      const int64_t ctas = cdiv(inner, kMarchCols) * outer;
-      const int64_t want = (512 / (G * kMarchCols / 2)) * (int64_t)num_sms();
-      int nseg = 1;
-      if (ctas < want) {
-        nseg = (int)cdiv(want, ctas);
-        const int max_seg = (int)cdiv(n_axis, 4 * STEP);
-        if (nseg > max_seg) nseg = max_seg;
-        if (nseg < 1) nseg = 1;
-      }
-      const int seg_len = (int)cdiv(cdiv(n_axis, nseg), STEP) * STEP;
-      dim3 grid((unsigned)cdiv(inner, kMarchCols), (unsigned)cdiv(n_axis, seg_len), (unsigned)outer);
-      kern<<<grid, G * kMarchCols / 2, smem, st>>>(in0, in1, out0, out1, n_axis, inner,
-                                              (int64_t)n_axis * inner, w, scale, seg_len);
-      MMB_CHECK_LAUNCH();
-      return MMB_OK;
+      // thin volumes (the 12-plane trailing chunk row): half-size steps, so that 12 of 16
+      // rows of a step are outputs instead of 12 of 32
+      if (n_axis <= 16)
+        return march<R, 2>(in0, in1, out0, out1, n_axis, inner, outer, w, scale, st);
+      return march<R, MMB_MARCH_G>(in0, in1, out0, out1, n_axis, inner, outer, w, scale, st);
     }
   }
   if constexpr (R > 20 && R <= 32) {      // wider radii: direct kernel below
