@@ -191,8 +191,9 @@ def roofline_block(ms, cnt, units):
         if dom in tj["kernels"]:
             vox_per_launch = units[kinds.index(dom)] / per_kind[dom]["launches"]
             traffic = tj["kernels"][dom]["dram_bytes_per_voxel"] * vox_per_launch
-            traffic_src = (f"dram__bytes_read.sum + dram__bytes_write.sum per voxel from "
-                           f"profiles/{name} x this run's voxels per launch")
+            traffic_src = (f"dram__bytes_read.sum + dram__bytes_write.sum per voxel of a 505^3 "
+                           f"chunk from profiles/{name} x this run's voxels per launch (the "
+                           f"same file holds a 12x505x505 thin chunk, whose output stays in L2)")
             break
     return {"bound": "hbm", "kernel": dom, "achieved": per_kind[dom]["gbps"],
             "peak": peaks["hbm_gbs"], "unit": "GB/s",
