@@ -550,3 +550,32 @@ def test_detect_blobs_other_integer_dtypes_follow_img_as_float():
         got = detector.detect_blobs(roi, [0])
         assert want is not None and len(want) > 10
         assert len(set(_rows(got)) ^ set(_rows(want))) <= max(1, len(want) // 200), dt
+
+
+def test_streamed_stack_with_overflowing_candidate_buffers(tmp_path):
+    """A host stack streamed as five y-strips through a workspace whose candidate
+    buffers overflow on the first chunks (capacity 8): every overflowing chunk is redone
+    from its strip, which may only be handed back to the feeder once all of its chunks
+    are collected - same table as the resident run with ample buffers."""
+    from magellanmapper_b200 import gpu
+    shape = (40, 170, 64)
+    vol, _ = synth.make_volume(shape, seed=77, density=1 / 1500.0)
+    _setup(near_max=synth.near_max_of(vol), segment_size=35)
+    os.chdir(tmp_path)
+
+    def run(img):
+        _, _, b = stack_detect.detect_blobs_blocks(
+            str(tmp_path / "ov"), np_io.Image5d(img[None]), None, None, [0], False, False, True)
+        return b.blobs
+    want = run(torch.from_numpy(vol.view(np.int16)).cuda())
+    stack_detect.StackDetector.release_workspace()
+    settings = config.get_roi_profile(0)
+    blocks = stack_detect.setup_blocks(settings, shape)
+    assert blocks.sub_roi_slices.shape[1] >= 4          # at least four strips, two buffers
+    largest = [max(s[a].stop - s[a].start for s in blocks.sub_roi_slices.flat) for a in range(3)]
+    small = gpu.ChunkDetector(tuple(largest), capacity=8)
+    stack_detect.StackDetector._gpu_detector = small
+    got = run(vol)
+    assert small.capacity > 8                           # buffers were regrown on overflow
+    assert len(want) > 100
+    np.testing.assert_array_equal(got, want)
