@@ -166,7 +166,7 @@ def collect_profile(lib):
     return ms, cnt, units
 
 
-def roofline_block(ms, cnt, units):
+def roofline_block(ms, cnt, units, sm_mhz=None):
     """Roofline of the dominant kernel (the y sweep: 8 B in + 8 B out per voxel) from the
     CUDA events the library records around every launch on the launching stream."""
     peaks, peak_src = peaks_json()
@@ -195,7 +195,27 @@ def roofline_block(ms, cnt, units):
                            f"chunk from profiles/{name} x this run's voxels per launch (the "
                            f"same file holds a 12x505x505 thin chunk, whose output stays in L2)")
             break
+    # the fused x -> y sweep is bound by the FP32 pipe, not by HBM: report its pipe fraction
+    # next to the HBM figure the contract asks for, and the HBM-bound sweep (z) as well
+    fp32 = None
+    if "log_xy" in per_kind:
+        clock = (sm_mhz or 1965.0) * 1e6
+        lane_fma = 165.0          # (10 r + 5) per voxel, mean over the sigma 3..5 ladder (r = 12..20)
+        k = per_kind["log_xy"]
+        rate = lane_fma * units[kinds.index("log_xy")] / (k["ms"] * 1e-3)
+        fp32 = {"kernel": "log_xy", "lane_fma_per_voxel": lane_fma,
+                "achieved_tflops": 2 * rate / 1e12,
+                "peak_tflops": 2 * 148 * 128 * clock / 1e12,
+                "frac": rate / (148 * 128 * clock),
+                "note": "direct-form arithmetic (10 r + 5 FMAs per voxel) over the pipe peak of "
+                        "128 lane-FMAs per clock per SM at the sampled SM clock; the x taps "
+                        "run in the symmetric-pair form, so fewer pipe slots are issued"}
+    hbm_kernel = None
+    if "log_z" in per_kind:
+        hbm_kernel = {"kernel": "log_z", "achieved": per_kind["log_z"]["gbps"],
+                      "frac": per_kind["log_z"]["gbps"] / peaks["hbm_gbs"]}
     return {"bound": "hbm", "kernel": dom, "achieved": per_kind[dom]["gbps"],
+            "fp32_pipe": fp32, "largest_hbm_bound_kernel": hbm_kernel,
             "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": per_kind[dom]["gbps"] / peaks["hbm_gbs"], "traffic": traffic,
             "traffic_source": traffic_src,
@@ -205,10 +225,11 @@ def roofline_block(ms, cnt, units):
             "avg_launch_ms": per_kind[dom]["ms"] / per_kind[dom]["launches"],
             "algorithmic_bytes_per_voxel": alg_bytes[dom],
             "units": "true voxels (X, not the padded row pitch) of rank 0's launches",
-            "fp32_colimit": "the three sweeps execute (14 r + 7) fp32 FMAs per voxel per scale "
-                            "(r = 12..20) as packed FFMA2; at the 128 lane-FMA/clk/SM pipe peak "
-                            "that alone takes as long as moving the algorithmic bytes at the "
-                            "measured HBM peak (DESIGN.md section 4)",
+            "fp32_colimit": "one LoG scale costs (14 r + 7) fp32 FMAs per voxel (r = 12..20) as "
+                            "packed FFMA2; at the 128 lane-FMA/clk/SM pipe peak that alone takes "
+                            "as long as moving the 40 B/voxel of three separate sweeps at the "
+                            "measured HBM peak, so x and y run fused (12 B/voxel, FP32-bound: see "
+                            "fp32_pipe) and z stays the HBM-side sweep (DESIGN.md section 4)",
             "per_kernel": per_kind}
 
 
@@ -496,7 +517,7 @@ def main_named(args, shape, cores):
                                                  and np.array_equal(b, final))}
             del host, host_np
 
-    roof = roofline_block(ms, cnt, units)
+    roof = roofline_block(ms, cnt, units, clocks.get("sm_mhz"))
     cpu = None
     if not args.skip_cpu:
         if args.config == 1:
@@ -786,7 +807,7 @@ def main():
             dist.destroy_process_group()
         return
 
-    roof = roofline_block(ms, cnt, units)
+    roof = roofline_block(ms, cnt, units, clocks and clocks.get("sm_mhz"))
 
     cpu = None
     if not args.skip_cpu:
