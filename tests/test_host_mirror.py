@@ -355,3 +355,25 @@ def test_setup_images_opens_reference_written_files(golden_dir):
     np.testing.assert_array_equal(sub.img[0], img5d.img[0, 1:4, 4:24, 5:15])
     with pytest.raises(FileNotFoundError):
         nio.setup_images(os.path.join(golden_dir, "feed", "absent"))
+
+
+def test_sigma_ladder_is_scikit_images_own_form():
+    """``blob_log`` builds its ladder as ``linspace(0, 1, n) * (max - min) + min``, which is
+    not ``linspace(min, max, n)`` in the last bits unless ``max - min`` is a power of two:
+    product, oracle and the radius column (sigma * sqrt(3)) follow scikit-image's form."""
+    from oracle import skimage_restated as ski
+    from magellanmapper_b200.cv import detector
+    from magellanmapper_b200.settings import roi_prof
+    for lo, hi, n in ((3, 5, 10), (4, 10, 10), (1, 50, 7), (10, 14, 10)):
+        want = np.linspace(0, 1, n) * (np.float64(hi) - np.float64(lo)) + np.float64(lo)
+        np.testing.assert_array_equal(ski.sigma_list(lo, hi, n), want)
+        prof = roi_prof.ROIProfile()
+        prof["min_sigma_factor"], prof["max_sigma_factor"], prof["num_sigma"] = lo, hi, n
+        np.testing.assert_array_equal(detector.sigma_ladder(prof, 1.0), want)
+    # the case the plain linspace gets wrong (config 4's second channel)
+    plain = np.linspace(4, 10, 10)
+    assert np.max(np.abs(plain - ski.sigma_list(4, 10, 10))) > 0
+    # a float32 image rounds the ends and their difference to float32 first
+    f32 = detector.skimage_ladder(np.float32(3.3), np.float32(5.7), 10)
+    want32 = np.linspace(0, 1, 10) * (np.float32(5.7) - np.float32(3.3)) + np.float32(3.3)
+    np.testing.assert_array_equal(f32, want32.astype(np.float64))
