@@ -351,6 +351,9 @@ def prune_seams(master_zyx: torch.Tensor, check_zyx: torch.Tensor, tol: Sequence
 #: local maxima, survivors of the overlap pruning, and the size of the set whose survival
 #: in scikit-image depends on its pair iteration order
 STATS = {"peaks": 0, "survivors": 0, "order_dependent": 0}
+#: developer aid: when a list, every collected chunk appends its status counters
+#: (local maxima, survivors, kill edges, order-dependent set) - tools/side_stream_check.py
+CHUNK_LOG = None
 
 
 class _Slot:
@@ -487,6 +490,8 @@ class ChunkDetector:
         STATS["peaks"] += n_peaks
         STATS["survivors"] += n_out
         STATS["order_dependent"] += n_od
+        if CHUNK_LOG is not None:
+            CHUNK_LOG.append((tuple(ticket.args[0].shape), n_peaks, n_out, n_edges, n_od))
         # copy on the stream the chunk ran on: the slot may then be reused by a later
         # chunk of that stream right away (consumers on another stream must order
         # themselves after it)

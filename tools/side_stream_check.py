@@ -25,13 +25,23 @@ bench.setup_config(nm, tmp + "/c2")
 def run(img):
     _, _, b = stack_detect.detect_blobs_blocks(tmp + "/c2", np_io.Image5d(img[None]), None, None, [0], False, False, True)
     return b.blobs
+from magellanmapper_b200 import gpu
+gpu.CHUNK_LOG = []
 ref = run(vol)
+ref_log = list(gpu.CHUNK_LOG)
 print("ref rows", ref.shape)
 stack_detect.THIN_CHUNK_FRACTION = 0.3
 bad = 0
 for i in range(12):
+    gpu.CHUNK_LOG = []
     v = run(vol)
     d = int(np.count_nonzero(np.any(v != ref, axis=1))) if v.shape == ref.shape else -1
     bad += d != 0
     print(i, d, end="; ")
+    if d != 0:
+        # which chunks differ, and already in the number of local maxima (before pruning)?
+        a = sorted(ref_log)
+        b = sorted(gpu.CHUNK_LOG)
+        diff = [(x, y) for x, y in zip(a, b) if x != y]
+        print("\n   chunks whose counters differ (shape, peaks, survivors, edges, od):", diff[:4])
 print("\nBAD RUNS", bad)
