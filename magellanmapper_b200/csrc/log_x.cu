@@ -142,11 +142,7 @@ conv_x_tma_kernel(const __grid_constant__ CUtensorMap tm_in,
     }
     // the previous tile's stores must have finished reading the output boxes
     if (tid == 0) tma_wait_read<0>();
-    __syncthreads();                 // every window is in registers: the stage is free
-    if (tid == 0) {
-      const int64_t tn = t + (int64_t)kXStages * gridDim.x;
-      if (tn < n_tiles) issue_load(tn, stage);
-    }
+    __syncthreads();
     if (active) {
       // scatter form: one window value feeds every output it touches, so it stays
       // in the operand-reuse cache across the FFMAs and each FFMA reads a single
@@ -171,6 +167,11 @@ conv_x_tma_kernel(const __grid_constant__ CUtensorMap tm_in,
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
+      // every window value of this tile has been consumed by the arithmetic above: only now
+      // may the stage be refilled (a barrier right after the window copy does not order
+      // reads still in flight against the async proxy)
+      const int64_t tn = t + (int64_t)kXStages * gridDim.x;
+      if (tn < n_tiles) issue_load(tn, stage);
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
         if (x0 + 32 * b < X) {
@@ -326,11 +327,12 @@ conv_x_ws_kernel(const __grid_constant__ CUtensorMap tm_in,
           }
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_in[s]);         // the slot may be refilled
-
       float2 acc[16];
       x_taps_sym<R, G::R4, G::W>(win, acc, w);
+      // the slot may be refilled only once every window value has been consumed: an arrival
+      // right after the window copy would not wait for reads still in flight
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_in[s]);
 
 #ifdef MMB_WS_DIRECT
       {

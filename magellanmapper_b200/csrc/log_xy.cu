@@ -9,8 +9,7 @@
 //   x phase  (the tile arithmetic of conv_x_tma_kernel): the 32-row x (128 + 2 R4)-column
 //            window of F arrives by TMA (32 x 32-float boxes, 128-byte swizzle, zero fill
 //            outside the plane, scipy 'reflect' patched in at the x faces); thread (lane =
-//            row, warp = 16-output segment) copies its window to registers - which frees the
-//            single input stage for the TMA load of the next tile - scatters every value into
+//            row, warp = 16-output segment) copies its window to registers, scatters every value into
 //            the outputs it touches (FFMA2 on the (A, B) pair with the (g, h) weight pair as
 //            the uniform operand) and writes A and B rows into a shared-memory RING;
 //   y phase  (the arithmetic of conv_march_kernel<MID>): thread (column pair, row group)
@@ -204,10 +203,14 @@ conv_xy_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __r
         win[4 * c + 0] = v.x; win[4 * c + 1] = v.y; win[4 * c + 2] = v.z; win[4 * c + 3] = v.w;
       }
     }
-    // every window is in registers (the stage is free) and every thread has finished the
-    // previous y phase (the ring rows this tile replaces are free)
+    // every thread has finished the previous y phase: the ring rows this tile replaces are
+    // free.  The TMA load of the NEXT tile into the (single) stage is NOT issued here: a
+    // barrier orders the window reads above only among the threads, not against the async
+    // proxy, and a read still in flight when the bulk copy lands would return the next
+    // tile's rows (seen as run-to-run differences of a few blobs per chunk whenever other
+    // work shared the SMs: tools/concurrency_probe.py).  It is issued after the barrier that
+    // follows the arithmetic, by which every window value has been consumed.
     __syncthreads();
-    if (tid == 0 && j + 1 < ntiles) issue_load(j + 1);
     const int row = org + lane;
     if (x_active && row >= row_first) {
       float2 acc[16];
@@ -239,11 +242,16 @@ conv_xy_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __r
   for (int j = 0; j < ntiles; ++j) {
     x_phase(j);
     const int s = j - G::P;
+    if (s < 0) {
+      // prologue tile: no y phase follows, so the barrier that proves every window value
+      // consumed is this one
+      __syncthreads();
+      if (tid == 0 && j + 1 < ntiles) { fence_proxy_async(); issue_load(j + 1); }
+    }
     if (j == G::P - 1) {
       // 'reflect' rows the prologue covers: above the first row, and - for a segment that
       // starts within RP rows of the end - below the last one
       if (row_first < 0 || a0 + RP > Y) {
-        __syncthreads();
         if (row_first < 0) mirror_rows(row_first, min(0, a0 + RP));
         if (a0 + RP > Y) mirror_rows(Y, min(a0 + RP, Y + R));
       }
@@ -257,6 +265,8 @@ conv_xy_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __r
       if (q_hi > q_lo) mirror_rows(q_lo, q_hi);
     }
     __syncthreads();                                     // the ring rows of this step are in
+    // ... and every window of this tile has been consumed: the stage may be refilled
+    if (tid == 0 && j + 1 < ntiles) { fence_proxy_async(); issue_load(j + 1); }
     const int a_out = a0 + kFRows * s + grp * 8;
     if (y_active && a_out < a_end) {
       float2 acc0[8], acc1[8];

@@ -16,6 +16,7 @@
 // with 'nearest' padding each 1-D pass is a dense n x n matrix built on the
 // host), unsharp, erosion, and one write of float32.
 #include <math.h>
+#include <stdlib.h>
 #include <type_traits>
 #include <vector>
 #include <map>
@@ -426,7 +427,8 @@ int preprocess_impl(const void* in, int dtype, const int64_t st[3], int Z, int Y
   bz = bz < Z ? bz : Z; by = by < Y ? by : Y; bx = bx < X ? bx : X;
   // float64 input: the shared-memory kernel holds the block as float32, which would take the
   // percentiles of ROUNDED samples; the global-memory path selects on the float64 keys
-  if (bz > 32 || by > 32 || bx > 32 || dtype == MMB_F64) {
+  static const bool debug_large = getenv("MMB_DEBUG_PRE_LARGE") != nullptr;   // developer bisect
+  if (bz > 32 || by > 32 || bx > 32 || dtype == MMB_F64 || debug_large) {
     // blocks that do not fit one CTA's shared memory: global-memory path
     if (scratch_bytes < preprocess_large_work_bytes(Z, Y, pitch, bz, by, bx)) scratch = nullptr;
     return preprocess_large_impl(in, dtype, st, Z, Y, X, bz, by, bx, p, out, pitch, scratch, s);
