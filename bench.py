@@ -437,6 +437,9 @@ def main_named(args, shape, cores):
                 False, True)
         return None if b is None else b.blobs
 
+    # the named configurations are measured on one stream (their committed lines under
+    # profiles/ were), so that every event duration is of a kernel alone on the device
+    stack_detect.THIN_CHUNK_FRACTION = 0.0
     lib.mmb_profile_enable(1)
     for _ in range(args.warmup):
         final = run(vol, "res")
@@ -738,6 +741,30 @@ def main():
     ms, cnt, units = collect_profile(lib)
     clocks = sampler.stop() if rank == 0 else None
 
+    # The resident single-GPU call runs the thin trailing chunks on a side stream, under the
+    # kernels of the full chunks.  Events around a launch that shares the SMs with another
+    # launch time the pair, not the kernel, so the roofline's durations come from the same
+    # number of further steps of the same workload with that side stream off (one stream,
+    # every kernel alone on the device); the overlapped region's figures are kept beside them.
+    overlapped = None
+    side_on = world == 1 and not seamless and stack_detect.THIN_CHUNK_FRACTION > 0
+    if side_on:
+        overlapped = (ms, cnt, units)
+        frac_side = stack_detect.THIN_CHUNK_FRACTION
+        stack_detect.THIN_CHUNK_FRACTION = 0.0
+        try:
+            step_resident()
+            torch.cuda.synchronize()
+            lib.mmb_profile_enable(1)
+            t1 = time.perf_counter()
+            for _ in range(args.steps):
+                step_resident()
+            torch.cuda.synchronize()
+            one_stream_ms = (time.perf_counter() - t1) / args.steps * 1e3
+            ms, cnt, units = collect_profile(lib)
+        finally:
+            stack_detect.THIN_CHUNK_FRACTION = frac_side
+
     # a step ends with host-side table assembly, so the step time is the larger of
     # the device span and the wall clock between the two synchronisations
     t_step = max(wall, dev_ms / 1e3)
@@ -808,6 +835,18 @@ def main():
         return
 
     roof = roofline_block(ms, cnt, units, clocks and clocks.get("sm_mhz"))
+    if overlapped is not None:
+        o = roofline_block(*overlapped, clocks and clocks.get("sm_mhz"))
+        roof["timed_on"] = (
+            f"{args.steps} further steps of the same resident workload on one stream "
+            f"({one_stream_ms:.1f} ms per step); the region `value` is timed on runs the "
+            "thin chunks on a side stream, where the events around a launch also span the "
+            "launch it shares the SMs with (overlapped_region)")
+        roof["overlapped_region"] = {
+            "kernel": o["kernel"], "achieved": o["achieved"], "frac": o["frac"],
+            "avg_launch_ms": o["avg_launch_ms"],
+            "sum_of_event_ms_per_step": sum(v["ms"] for v in o["per_kernel"].values()) / args.steps,
+            "ms_per_step": t_step / args.steps * 1e3}
 
     cpu = None
     if not args.skip_cpu:

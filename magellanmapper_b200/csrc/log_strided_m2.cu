@@ -56,15 +56,6 @@ static int run(const float* in0, const float* in1, float* out0, float* out1, int
   ProfScope ps(outer == 1 ? PROF_LOG_Z : PROF_LOG_Y, (double)inner * n_axis * outer, st);
   const uintptr_t bits = (uintptr_t)in0 | (uintptr_t)in1 | (uintptr_t)out0 | (uintptr_t)out1;
   const bool aligned = (bits & 15) == 0 && inner % 4 == 0;
-  // developer bisect (tools/concurrency_probe.py): the plain one-thread-per-column kernel
-  static const bool simple = getenv("MMB_DEBUG_Z_SIMPLE") != nullptr;
-  if (simple) {
-    dim3 grid((unsigned)cdiv(inner, kThreads), (unsigned)cdiv(n_axis, kNB), (unsigned)outer);
-    conv_strided_kernel<R, 2, kNB, kThreads><<<grid, kThreads, 0, st>>>(
-        in0, in1, out0, out1, n_axis, inner, (int64_t)n_axis * inner, w, scale);
-    MMB_CHECK_LAUNCH();
-    return MMB_OK;
-  }
   if constexpr (R <= 20) {
     if (aligned) {
       // thin volumes (the 12-plane trailing chunk row): half-size steps, so that 12 of 16

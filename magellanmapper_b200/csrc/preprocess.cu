@@ -427,8 +427,7 @@ int preprocess_impl(const void* in, int dtype, const int64_t st[3], int Z, int Y
   bz = bz < Z ? bz : Z; by = by < Y ? by : Y; bx = bx < X ? bx : X;
   // float64 input: the shared-memory kernel holds the block as float32, which would take the
   // percentiles of ROUNDED samples; the global-memory path selects on the float64 keys
-  static const bool debug_large = getenv("MMB_DEBUG_PRE_LARGE") != nullptr;   // developer bisect
-  if (bz > 32 || by > 32 || bx > 32 || dtype == MMB_F64 || debug_large) {
+  if (bz > 32 || by > 32 || bx > 32 || dtype == MMB_F64) {
     // blocks that do not fit one CTA's shared memory: global-memory path
     if (scratch_bytes < preprocess_large_work_bytes(Z, Y, pitch, bz, by, bx)) scratch = nullptr;
     return preprocess_large_impl(in, dtype, st, Z, Y, X, bz, by, bx, p, out, pitch, scratch, s);

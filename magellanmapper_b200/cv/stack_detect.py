@@ -34,16 +34,14 @@ _logger = config.logger.getChild(__name__)
 DEVICE_TABLES = True
 
 
-#: EXPERIMENTAL, off, and not used by any reported result: chunks with at most this fraction
-#: of the largest chunk's voxels run on a side stream under the kernels of the full chunks
-#: (0 = off, the default).  Measured on config 2
-#: with 0.3: 329 -> 319 ms per stack.  OFF because with a device-resident image the two
-#: streams run unsynchronised for a whole stack and the tables of a few thin chunks then
-#: vary from run to run (a handful of rows, occasionally the row count:
-#: tools/side_stream_check.py), which breaks the bit-for-bit reproducibility the tests
-#: demand; serialising the streams removes it, routing every workspace read through L2
-#: and waiting for TMA-store completion do not.  Unresolved: see DESIGN.md.
-THIN_CHUNK_FRACTION = 0.0
+#: Chunks with at most this fraction of the largest chunk's voxels (the thin trailing chunks
+#: of a grid: 4-7 % of the voxels, 12 % of the step when run alone) go to a side stream with
+#: their own small workspace, under the kernels of the full chunks.  Used for a
+#: device-resident image on one GPU (the streamed-host and multi-GPU calls keep one stream).
+#: Off until round 2's fix of the TMA stage refill (csrc/log_xy.cu, log_x.cu): the run-to-run
+#: differences this route showed were that race, which any concurrent work exposed
+#: (tools/concurrency_probe.py, tools/side_stream_check.py: 12 of 12 runs identical now).
+THIN_CHUNK_FRACTION = 0.3
 
 
 class StackTimes(Enum):
@@ -277,7 +275,8 @@ class StackDetector(object):
         import torch
         nvox = {c: int(np.prod([s.stop - s.start for s in sub_roi_slices[c]])) for c in todo}
         big = max(nvox.values()) if nvox else 0
-        thin = {c for c in todo if THIN_CHUNK_FRACTION > 0 and nvox[c] <= THIN_CHUNK_FRACTION * big}
+        use_side = THIN_CHUNK_FRACTION > 0 and coords is None and feeder is None
+        thin = {c for c in todo if use_side and nvox[c] <= THIN_CHUNK_FRACTION * big}
         thin_det, side, main = None, None, torch.cuda.current_stream()
         if thin and len(thin) < len(todo):
             tshape = tuple(max(sub_roi_slices[c][a].stop - sub_roi_slices[c][a].start for c in thin)
