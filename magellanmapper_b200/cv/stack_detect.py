@@ -42,6 +42,10 @@ DEVICE_TABLES = True
 #: differences this route showed were that race, which any concurrent work exposed
 #: (tools/concurrency_probe.py, tools/side_stream_check.py: 12 of 12 runs identical now).
 THIN_CHUNK_FRACTION = 0.3
+#: The same for a host image that is streamed strip by strip: results equal (8 of 8 runs), but
+#: 320 instead of 278 ms per config-2 stack, because every strip hand-over joins the two
+#: streams (tools/side_stream_host_check.py) - off.
+THIN_SIDE_FOR_HOST_IMAGES = False
 
 
 class StackTimes(Enum):
@@ -269,13 +273,14 @@ class StackDetector(object):
         pending = deque()
 
         # The trailing chunks of a grid are thin (12 planes, or 48 voxels wide in
-        # config 2): 4 % of the voxels but 15 % of the kernel time when they run alone,
+        # config 2): 7 % of the voxels but 12 % of the step when they run alone,
         # because their launches cannot fill the GPU.  They get their own small
         # workspace and run on a side stream, under the kernels of the full chunks.
         import torch
         nvox = {c: int(np.prod([s.stop - s.start for s in sub_roi_slices[c]])) for c in todo}
         big = max(nvox.values()) if nvox else 0
-        use_side = THIN_CHUNK_FRACTION > 0 and coords is None and feeder is None
+        use_side = (THIN_CHUNK_FRACTION > 0 and coords is None
+                    and (feeder is None or THIN_SIDE_FOR_HOST_IMAGES))
         thin = {c for c in todo if use_side and nvox[c] <= THIN_CHUNK_FRACTION * big}
         thin_det, side, main = None, None, torch.cuda.current_stream()
         if thin and len(thin) < len(todo):
@@ -348,14 +353,10 @@ class StackDetector(object):
             if strip_of is not None:
                 in_flight[strip_of] = in_flight.get(strip_of, 0) + 1
             if coord in thin:
-                if os.environ.get("MMB_SIDE_SERIAL"):
-                    side.wait_stream(main)
                 with torch.cuda.stream(side):
                     pending.append((cls.enqueue_sub_roi(
                         coord, sub_rois_offsets[coord], last_coord, denoise_max_shape, None,
                         sub, channel, False, det=thin_det), strip_of))
-                if os.environ.get("MMB_SIDE_SERIAL"):
-                    main.wait_stream(side)
             else:
                 pending.append((cls.enqueue_sub_roi(
                     coord, sub_rois_offsets[coord], last_coord, denoise_max_shape, None,
