@@ -181,3 +181,17 @@ def test_isotropic_and_unmixing(golden_dir):
     prof = mm.Profile(isotropic=(0.96, 1, 1), segment_size=40, exclude_border=(1, 0, 0))
     final = mm.detect_blobs_blocks(g["svol"], prof, (2.5, 1, 1), float(g["snm"]))
     np.testing.assert_array_equal(final, g["stack_iso_blobs"])
+
+
+def test_colocalize_blobs(golden_dir):
+    """``colocalize_blobs`` (ball(2) label dilation, "min" and percentile thresholds, blobs
+    sharing a voxel, on the ROI faces and outside the ROI) against the unmodified reference,
+    on raw uint16 and on preprocessed float64 intensities."""
+    g = _load(golden_dir, "coloc.npz")
+    for key, roi, thresh in (("min_raw", g["roi"], None), ("p5_raw", g["roi"], 5),
+                             ("min_pre", g["pre"], None), ("p30_pre", g["pre"], 30)):
+        got = mm.colocalize_blobs(roi, g["blobs"], thresh)
+        assert got.dtype == np.uint8
+        np.testing.assert_array_equal(got, g[key], err_msg=key)
+    assert mm.colocalize_blobs(g["roi"][..., 0], g["blobs"]) is None
+    assert mm.colocalize_blobs(g["roi"], None) is None
