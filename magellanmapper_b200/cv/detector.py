@@ -15,7 +15,7 @@ from typing import Callable, Dict, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
 
-from ..io import libmag, np_io
+from ..io import libmag, np_io, npz_writer
 from ..plot import plot_3d
 from ..settings import config
 
@@ -170,8 +170,9 @@ class Blobs:
                 arc = np_io.read_np_archive(archive)
                 arc.update(to_add)
         libmag.backup_file(self.path)
-        with open(self.path, "wb") as f:
-            np.savez(f, **arc)
+        # numpy.savez's format, written by a few threads (io/npz_writer.py): the table of a
+        # whole stack is the longest host-side stage after the detection itself
+        npz_writer.savez(self.path, arc, add_suffix=False)
         return arc
 
     # -- column accessors -----------------------------------------------------------
