@@ -139,3 +139,65 @@ def test_detect_blobs_blocks_random_stack(ns, seed):
     got = mm.detect_blobs_blocks(vol, mm.Profile(**mods), res, near_max)
     assert blobs.blobs is not None and len(blobs.blobs) > 10
     np.testing.assert_array_equal(got, blobs.blobs)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_make_isotropic_and_isotropic_detection_random(ns, seed):
+    """``make_isotropic`` (up- and down-scaling axes mixed, integer and float ROIs, one and
+    two channels) and ``detect_blobs`` with ``isotropic`` incl. the back-scaling of the blobs."""
+    from oracle import ref_shim
+    rng = np.random.default_rng(700 + seed)
+    shape = tuple(int(v) for v in (rng.integers(8, 24), rng.integers(30, 60), rng.integers(30, 60)))
+    res = tuple(float(v) for v in rng.choice([0.6, 1.0, 2.5, 4.0], 3))
+    iso = tuple(float(v) for v in rng.choice([0.5, 0.8, 1.0, 1.3], 3))
+    vol, _ = synth.make_volume(shape, seed=800 + seed, density=1 / 1200.0)
+    near_max = synth.near_max_of(vol)
+    ref_shim.set_profile(ns, res, near_max=near_max, isotropic=iso)
+    np.testing.assert_array_equal(mm.make_isotropic(vol, iso, res), ns.cv_nd.make_isotropic(vol, iso))
+    as_float = vol.astype(np.float64) / 65535
+    np.testing.assert_array_equal(mm.make_isotropic(as_float, iso, res),
+                                  ns.cv_nd.make_isotropic(as_float, iso))
+    two = np.stack([vol, vol[::-1]], axis=-1)
+    np.testing.assert_array_equal(mm.make_isotropic(two, iso, res), ns.cv_nd.make_isotropic(two, iso))
+    prof = mm.Profile(isotropic=iso)
+    np.testing.assert_array_equal(mm.detect_blobs(vol, prof, res), ns.detector.detect_blobs(vol, [0]))
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_colocalize_blobs_random(ns, seed):
+    rng = np.random.default_rng(900 + seed)
+    shape = tuple(int(v) for v in (rng.integers(10, 26), rng.integers(30, 50), rng.integers(30, 50)))
+    n_chl = int(rng.choice([2, 3]))
+    vols = [synth.make_volume(shape, seed=950 + 10 * seed + c, density=1 / 900.0)[0]
+            for c in range(n_chl)]
+    roi = np.stack(vols, axis=-1)
+    n = int(rng.integers(20, 150))
+    blobs = np.full((n, 11), -1.0)
+    blobs[:, :3] = rng.integers(-2, np.add(shape, 2), (n, 3))     # some outside the ROI
+    blobs[:, 3] = 5.0
+    blobs[:, 6] = rng.integers(0, n_chl, n)
+    blobs[: n // 8, :3] = blobs[n // 8: 2 * (n // 8), :3]         # shared voxels
+    for thresh in (None, 5, 60):
+        want = ns.colocalizer.colocalize_blobs(roi, blobs, thresh)
+        np.testing.assert_array_equal(mm.colocalize_blobs(roi, blobs, thresh), want)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_near_bounds_random(ns, seed):
+    from magmap.io import importer
+    rng = np.random.default_rng(1000 + seed)
+    multichannel = bool(seed % 2)
+    shape = (int(rng.integers(2, 7)), int(rng.integers(20, 70)), int(rng.integers(20, 70)))
+    if multichannel:
+        shape += (2,)
+    hi = int(rng.choice([255, 4000, 65535]))
+    vol = rng.integers(0, hi, shape).astype(np.uint8 if hi == 255 else np.uint16)
+    lows, highs = [], []
+    for z in range(shape[0]):
+        lo, hi_ = importer.calc_intensity_bounds(vol[z], dim_channel=2)
+        lows.append(lo)
+        highs.append(hi_)
+    want_min, want_max = importer.calc_near_intensity_bounds([], [], lows, highs)
+    got_min, got_max = mm.calc_near_bounds(vol, multichannel)
+    np.testing.assert_array_equal(np.ravel(got_min), np.ravel(want_min))
+    np.testing.assert_array_equal(np.ravel(got_max), np.ravel(want_max))
