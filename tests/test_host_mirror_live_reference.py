@@ -1,0 +1,92 @@
+"""The host-only helpers of the mirror (`Blobs` accessors and coordinate shifts, overlap and
+scaling factors, ROI selections, pruning ratios, sorting) against the UNMODIFIED reference on
+random tables - live, build container only (``/root/reference`` does not travel)."""
+import os
+
+import numpy as np
+import pytest
+
+from magellanmapper_b200.cv import detector
+from magellanmapper_b200.settings import config
+
+pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference/magmap"),
+                                reason="the unmodified reference is only in the build container")
+
+
+@pytest.fixture(scope="module")
+def ns():
+    from oracle import ref_shim
+    ref = ref_shim.load_reference()
+    ref.config.verbose = False
+    return ref
+
+
+def _tables(rng, n):
+    t = np.full((n, 4), 0.0)
+    t[:, :3] = rng.integers(0, 300, (n, 3))
+    t[:, 3] = rng.uniform(3, 9, n)
+    return t
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_blobs_accessors_and_shifts(ns, seed):
+    rng = np.random.default_rng(seed)
+    raw = _tables(rng, int(rng.integers(1, 200)))
+    ours, theirs = detector.Blobs(raw.copy()), ns.detector.Blobs(raw.copy())
+    assert ours.cols == theirs.cols
+    np.testing.assert_array_equal(ours.format_blobs(2), theirs.format_blobs(2))
+    assert ours.cols == theirs.cols
+    a, b = ours.blobs, theirs.blobs
+    off = rng.integers(-20, 20, 3)
+    fac = rng.uniform(0.3, 3, 3)
+    for name, arg in (("shift_blob_rel_coords", off), ("shift_blob_abs_coords", off),
+                      ("multiply_blob_rel_coords", fac), ("multiply_blob_abs_coords", fac)):
+        np.testing.assert_array_equal(getattr(detector.Blobs, name)(a, arg),
+                                      getattr(ns.detector.Blobs, name)(b, arg), err_msg=name)
+    for name in ("get_blob_confirmed", "get_blob_truth", "get_blobs_channel",
+                 "get_blob_abs_coords"):
+        np.testing.assert_array_equal(getattr(detector.Blobs, name)(a),
+                                      getattr(ns.detector.Blobs, name)(b), err_msg=name)
+    detector.Blobs.set_blob_truth(a, 1)
+    ns.detector.Blobs.set_blob_truth(b, 1)
+    detector.Blobs.set_blob_abs_coords(a, (4, 5, 6))
+    ns.detector.Blobs.set_blob_abs_coords(b, (4, 5, 6))
+    np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(detector.Blobs.blob_for_db(a[0]), ns.detector.Blobs.blob_for_db(b[0]))
+    for chl in (0, 2, [1, 2], None):
+        np.testing.assert_array_equal(detector.Blobs.blobs_in_channel(a, chl),
+                                      ns.detector.Blobs.blobs_in_channel(b, chl))
+    np.testing.assert_array_equal(detector.Blobs.replace_rel_with_abs_blob_coords(a.copy()),
+                                  ns.detector.Blobs.replace_rel_with_abs_blob_coords(b.copy()))
+    np.testing.assert_array_equal(ours.remove_abs_blob_coords(True),
+                                  theirs.remove_abs_blob_coords(True))
+    assert ours.cols == theirs.cols
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_roi_selection_sorting_ratios_and_factors(ns, seed):
+    rng = np.random.default_rng(50 + seed)
+    blobs = np.full((int(rng.integers(5, 400)), 11), -1.0)
+    blobs[:, :3] = rng.integers(0, 120, (len(blobs), 3))
+    blobs[:, 3] = rng.uniform(3, 9, len(blobs))
+    offset, size = rng.integers(0, 60, 3), rng.integers(1, 70, 3)
+    margin = rng.integers(0, 4, 3)
+    for kw in ({}, {"margin": margin}, {"reverse": False}, {"margin": margin, "reverse": False}):
+        got = detector.get_blobs_in_roi(blobs, offset, size, **kw)
+        want = ns.detector.get_blobs_in_roi(blobs, offset, size, **kw)
+        np.testing.assert_array_equal(got[0], want[0])
+        np.testing.assert_array_equal(got[1], want[1])
+    pad_a, pad_b = rng.integers(0, 10, 3), rng.integers(0, 10, 3)
+    np.testing.assert_array_equal(detector.get_blobs_interior(blobs, (120, 120, 120), pad_a, pad_b),
+                                  ns.detector.get_blobs_interior(blobs, (120, 120, 120), pad_a, pad_b))
+    got, want = detector.sort_blobs(blobs), ns.detector.sort_blobs(blobs)
+    np.testing.assert_array_equal(got[0], want[0])
+    np.testing.assert_array_equal(got[1], want[1])
+    for args in ((0, 0, 0), (10, 7, 12), (10, 10, 0), (5, 0, 9), (123, 100, 140)):
+        assert detector.meas_pruning_ratio(*args) == ns.detector.meas_pruning_ratio(*args)
+    res = [[float(v) for v in rng.choice([0.5, 0.913, 1.0, 2.5, 6.6], 3)]]
+    config.resolutions = res
+    ns.config.resolutions = res
+    np.testing.assert_array_equal(detector.calc_scaling_factor(), ns.detector.calc_scaling_factor())
+    for factor in (None, 2, 7):
+        np.testing.assert_array_equal(detector.calc_overlap(factor), ns.detector.calc_overlap(factor))
