@@ -63,6 +63,17 @@ class ROIProfile(profiles.SettingsDict):
         "register": dict(unsharp_strength=1.5),
         "atlas": dict(clip_vmax=97),
         "spawn": dict(mp_start="spawn"),
+        # display-only modifiers (roi_prof.py:223-330): nothing on the detection path reads
+        # their keys, but a profile string that names them must layer and be recorded in
+        # ``settings_name`` as the reference records it
+        "isotropic": dict(points_3d_thresh=0.3, isotropic_vis=(1, 1, 1)),
+        "contrast": dict(channel_colors=("inferno", "inferno"), scale_bar_color="w"),
+        "bone": dict(channel_colors=("bone", "bone"), scale_bar_color="w"),
+        "diverging": dict(channel_colors=("RdBu", "BrBG"), scale_bar_color="k",
+                          colorbar=dict(shrink=0.7)),
+        "randomcolors": dict(channel_colors=[]),
+        "norm": dict(norm=(0.0, 1.0)),
+        "rot180": dict(load_rot90=2),
     }
 
     def __init__(self, *args, **kwargs):

@@ -90,3 +90,43 @@ def test_roi_selection_sorting_ratios_and_factors(ns, seed):
     np.testing.assert_array_equal(detector.calc_scaling_factor(), ns.detector.calc_scaling_factor())
     for factor in (None, 2, 7):
         np.testing.assert_array_equal(detector.calc_overlap(factor), ns.detector.calc_overlap(factor))
+
+
+def _plain(v):
+    """Profile values as comparable plain objects (enums by name, dicts recursively)."""
+    if isinstance(v, dict):
+        return {str(getattr(k, "name", k)): _plain(x) for k, x in v.items()}
+    if isinstance(v, (list, tuple, np.ndarray)):
+        return [_plain(x) for x in v]
+    if hasattr(v, "name") and hasattr(v, "value") and not isinstance(v, (int, float)):
+        return v.name
+    return v
+
+
+def test_every_roi_profile_modifier_layers_like_the_reference(ns):
+    """``ROIProfile`` defaults, every named modifier on its own and in the combinations the
+    reference's documentation uses, plus the YAML profile: equal on every key the mirror
+    carries (the keys this path reads)."""
+    from magellanmapper_b200.settings import roi_prof
+    ref_default = ns.roi_prof.ROIProfile()
+    names = sorted(ref_default.profiles)
+    assert names, "the reference lists no modifiers"
+    ours_default = roi_prof.ROIProfile()
+    assert sorted(ours_default.profiles) == names
+    combos = [n for n in names] + ["lightsheet,4xnuc", "lightsheet,cleared,zebrafish",
+                                   "2p20x,lowres", "roi_blobs.yaml", "lightsheet,roi_blobs.yaml"]
+    cwd = os.getcwd()
+    os.chdir("/root/reference")          # the reference resolves YAML files under ./profiles
+    try:
+        for combo in [""] + combos:
+            theirs = ns.roi_prof.ROIProfile()
+            ours = roi_prof.ROIProfile()
+            if combo:
+                theirs.add_profiles(combo)
+                ours.add_profiles(combo)
+            assert ours[ours.NAME_KEY] == theirs[theirs.NAME_KEY], combo
+            for key in ours:
+                assert key in theirs, (combo, key)
+                assert _plain(ours[key]) == _plain(theirs[key]), (combo, key)
+    finally:
+        os.chdir(cwd)
