@@ -51,3 +51,53 @@ def test_reference_unit_tests_pass_on_the_mirror(name):
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def _run_selected(ref_file, aliases, keep):
+    """Load one of the reference's test files with ``aliases`` bound and run the test
+    methods whose names ``keep`` accepts."""
+    saved = {}
+    pkgs = {"magmap"} | {full.rsplit(".", 1)[0] for full in aliases}
+    try:
+        for pkg in sorted(pkgs):
+            saved[pkg] = sys.modules.get(pkg)
+            mod = types.ModuleType(pkg)
+            mod.__path__ = []
+            sys.modules[pkg] = mod
+        for full, mod in aliases.items():
+            saved[full] = sys.modules.get(full)
+            sys.modules[full] = mod
+            parent, leaf = full.rsplit(".", 1)
+            setattr(sys.modules[parent], leaf, mod)
+        spec = importlib.util.spec_from_file_location(
+            "_ref_" + os.path.basename(ref_file)[:-3], ref_file)
+        ref_tests = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref_tests)
+        suite = unittest.TestSuite()
+        for case in unittest.defaultTestLoader.loadTestsFromModule(ref_tests):
+            for t in case:
+                if keep(t.id().rsplit(".", 1)[1]):
+                    suite.addTest(t)
+        n = suite.countTestCases()
+        with open(os.devnull, "w") as sink:
+            result = unittest.TextTestRunner(stream=sink, verbosity=0).run(suite)
+        assert result.wasSuccessful(), result.failures + result.errors
+        return n
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def test_reference_np_io_and_libmag_unit_tests_on_the_mirror():
+    """``test_np_io.py`` whole, and of ``test_libmag.py`` the cases for the helpers this path
+    uses and the mirror therefore carries (path splitting and suffixing for the archive and
+    image-feed file names)."""
+    from magellanmapper_b200.io import libmag, np_io
+    assert _run_selected(os.path.join(REF_TESTS, "test_np_io.py"),
+                         {"magmap.io.np_io": np_io}, lambda name: True) == 1
+    mirrored = {"test_insert_before_ext", "test_splitext", "test_combine_paths"}
+    assert _run_selected(os.path.join(REF_TESTS, "test_libmag.py"),
+                         {"magmap.io.libmag": libmag}, mirrored.__contains__) == 3
