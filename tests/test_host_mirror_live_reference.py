@@ -130,3 +130,64 @@ def test_every_roi_profile_modifier_layers_like_the_reference(ns):
                 assert _plain(ours[key]) == _plain(theirs[key]), (combo, key)
     finally:
         os.chdir(cwd)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_csv_and_sqlite_sinks_random(ns, seed, tmp_path):
+    """Random blob tables (duplicates of the (roi, z, y, x) key, confirmed / truth flags,
+    several channels, several ROIs) through both implementations of the CSV and SQLite
+    sinks: the same CSV bytes and the same stored rows after inserts, replaces and deletes."""
+    import gzip
+    import importlib
+    from magellanmapper_b200.io import export_rois, sqlite
+    ref_export = importlib.import_module("magmap.io.export_rois")
+    ref_sqlite = importlib.import_module("magmap.io.sqlite")
+    rng = np.random.default_rng(70 + seed)
+    n = int(rng.integers(5, 400))
+    blobs = np.full((n, 11), -1.0)
+    blobs[:, :3] = rng.integers(0, 40, (n, 3))
+    blobs[:, 3] = np.round(rng.uniform(3, 9, n), 3)
+    blobs[:, 4] = rng.choice([-1, 0, 1], n)
+    blobs[:, 5] = rng.choice([-1, 0, 1, 2], n)
+    blobs[:, 6] = rng.integers(0, 3, n)
+    blobs[:, 7:10] = blobs[:, :3] + 100
+    dirs = {}
+    for tag in ("ours", "theirs"):
+        dirs[tag] = tmp_path / tag
+        dirs[tag].mkdir()
+    export_rois.blobs_to_csv(blobs, str(dirs["ours"] / "img.npy"))
+    ref_export.blobs_to_csv(blobs, str(dirs["theirs"] / "img.npy"))
+    texts = []
+    for tag in ("ours", "theirs"):
+        with gzip.open(dirs[tag] / "img_blobs.csv.gz", "rb") as f:
+            texts.append(f.read())
+    assert texts[0] == texts[1]
+
+    stored = []
+    for tag, mod, create in (("ours", sqlite, sqlite.create_db), ("theirs", ref_sqlite, ref_sqlite._create_db)):
+        conn, cur = create(str(dirs[tag] / "magmap.db"))
+        exp = mod.insert_experiment(conn, cur, "synth", None)
+        rois = [mod.select_or_insert_roi(conn, cur, exp, s, off, (30, 30, 30))[0]
+                for s, off in ((None, (1, 2, 3)), (0, (1, 2, 3)), (1, (4, 5, 6)))]
+        assert rois[0] == rois[1] != rois[2]
+        mod.insert_blobs(conn, cur, rois[0], blobs[:, :7])
+        mod.insert_blobs(conn, cur, rois[2], blobs[: n // 2, :7])
+        again = blobs[: n // 3, :7].copy()
+        again[:, 3] *= 2                                        # same key: replaced
+        mod.insert_blobs(conn, cur, rois[0], again)
+        n_del = mod.delete_blobs(conn, cur, rois[0], blobs[n // 4: n // 4 + 3])
+        cur.execute("SELECT {} FROM blobs ORDER BY roi_id, z, y, x, channel, radius".format(
+            mod._COLS_BLOBS))
+        rows = np.array([list(r) for r in cur.fetchall()], dtype=np.float64)
+        conf = mod.select_blobs_confirmed(cur, 1)
+        # the reference's `ClrDB.select_blobs_by_roi` (sqlite.py:823-836) spelled out
+        cur.execute("SELECT {}, id FROM blobs WHERE roi_id = ?".format(mod._COLS_BLOBS), (rois[2],))
+        got, ids = mod._parse_blobs(cur.fetchall())
+        if mod is sqlite:
+            same, same_ids = sqlite.select_blobs_by_roi(cur, rois[2])
+            np.testing.assert_array_equal(same, got)
+            assert same_ids == ids
+        stored.append((rows, n_del, np.asarray(conf), np.asarray(got), len(ids)))
+        conn.close()
+    for a, b in zip(stored[0], stored[1]):
+        np.testing.assert_array_equal(a, b)
