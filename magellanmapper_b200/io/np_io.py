@@ -84,10 +84,14 @@ def write_npy(image5d, md: Dict[Any, Any], path: str, find_near_bounds: bool = T
     """Save a ``t, z, y, x[, c]`` image as the reference's imported-image pair
     (np_io.py:787-862): ``near_min`` / ``near_max`` per channel from the per-plane 0.5 /
     99.5 percentiles (on the GPU, ``importer.calc_near_bounds``), the metadata file, and the
-    voxels plane by plane through a memory map.  ``md``: ``resolutions``, ``magnification``,
-    ``zoom``.  An existing image file is left alone."""
+    voxels plane by plane through a memory map.  ``md``: ``config.MetaKeys.RESOLUTIONS`` /
+    ``MAGNIFICATION`` / ``ZOOM`` (or the lower-case names as strings).  An existing image file is left alone."""
     import os
+    from enum import Enum
     from . import importer
+    # the reference keys the dictionary with `config.MetaKeys` members; plain lower-case
+    # names are accepted as well
+    md = {(k.name.lower() if isinstance(k, Enum) else k): v for k, v in md.items()}
     filename_image5d, filename_meta = importer.make_filenames(os.path.splitext(path)[0],
                                                               keep_ext=True)
     if os.path.exists(filename_image5d):

@@ -11,7 +11,8 @@ A caller of the reference sets these the same way and then calls
 from __future__ import annotations
 
 import logging
-from typing import List, Optional, Sequence
+from enum import Enum, auto
+from typing import Any, Dict, List, Optional, Sequence
 
 logger = logging.getLogger("magellanmapper_b200")
 
@@ -33,6 +34,20 @@ near_min: List[float] = [0.0]
 #: objective magnification and zoom of the loaded image (importer metadata)
 magnification = None
 zoom = None
+
+
+class MetaKeys(Enum):
+    """Keys of the image-import metadata dictionary (config.py:227-238), as
+    ``np_io.write_npy`` takes them."""
+    RESOLUTIONS = auto()
+    MAGNIFICATION = auto()
+    ZOOM = auto()
+    SHAPE = auto()
+    DTYPE = auto()
+
+
+#: metadata for image import (config.py:241-242)
+meta_dict: Dict[MetaKeys, Any] = dict.fromkeys(MetaKeys, None)
 
 SUFFIX_IMAGE5D = "image5d.npy"
 SUFFIX_META = "meta.yml"

@@ -191,3 +191,39 @@ def test_csv_and_sqlite_sinks_random(ns, seed, tmp_path):
         conn.close()
     for a, b in zip(stored[0], stored[1]):
         np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_write_npy_random_without_near_bounds(ns, seed, tmp_path):
+    """``np_io.write_npy`` keyed with ``config.MetaKeys`` like a reference caller keys it
+    (``find_near_bounds=False``: no GPU needed): the same ``.npy`` bytes and metadata file as
+    the reference's, and ``setup_images`` / ``load_metadata`` read back what it reads."""
+    import yaml
+    from magellanmapper_b200.io import np_io
+    rng = np.random.default_rng(90 + seed)
+    shape = (1, int(rng.integers(2, 9)), int(rng.integers(5, 40)), int(rng.integers(5, 40)))
+    if seed % 2:
+        shape += (int(rng.integers(2, 4)),)
+    dtype = [np.uint8, np.uint16, np.float32][seed % 3]
+    img = (rng.random(shape) * 200).astype(dtype)
+    res = [[float(v) for v in rng.choice([0.5, 1.1, 5.0], 3)]]
+    mag, zoom = float(rng.choice([5.0, 20.0])), float(rng.choice([0.8, 1.0]))
+    files = {}
+    for tag, mod, keys in (("ours", np_io, config.MetaKeys), ("theirs", ns.np_io, ns.config.MetaKeys)):
+        d = tmp_path / tag
+        d.mkdir()
+        md = {keys.RESOLUTIONS: res, keys.MAGNIFICATION: mag, keys.ZOOM: zoom}
+        mod.write_npy(img, md, str(d / "sample.czi"), False)
+        with open(d / "sample_image5d.npy", "rb") as f:
+            raw = f.read()
+        with open(d / "sample_meta.yml") as f:
+            meta = yaml.safe_load(f)
+        files[tag] = (raw, meta)
+    assert files["ours"][0] == files["theirs"][0]
+    assert files["ours"][1] == files["theirs"][1]
+    # the mirror reads the reference's pair
+    config.filename = None
+    img5d = np_io.setup_images(str(tmp_path / "theirs" / "sample"))
+    np.testing.assert_array_equal(np.asarray(img5d.img), img)
+    assert [list(r) for r in config.resolutions] == res
+    assert config.magnification == mag and config.zoom == zoom
