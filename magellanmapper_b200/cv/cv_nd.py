@@ -32,12 +32,19 @@ def edge_mode_for(shape: Sequence[int]) -> bool:
 
 
 def make_isotropic(roi, scale: Union[float, Sequence[float]] = 1,
-                   res: Optional[Sequence[float]] = None) -> np.ndarray:
+                   res: Optional[Sequence[float]] = None, **kwargs) -> np.ndarray:
     """Resize an ROI ``(z, y, x[, c])`` to be isotropic (cv_nd.py:1071-1106): linear
     interpolation with 'reflect' boundaries, Gaussian anti-aliasing on shrinking axes,
-    value range preserved and the result cast back to the ROI's dtype."""
+    value range preserved and the result cast back to the ROI's dtype.  ``kwargs`` are the
+    reference's overrides for ``rescale_resize``; the detection path passes none and only
+    the defaults are served."""
     from .. import gpu
     import torch
+    for key, val in kwargs.items():
+        if (key, val) not in (("preserve_range", True), ("order", 1), ("anti_aliasing", None)):
+            raise NotImplementedError(
+                f"make_isotropic({key}={val!r}): only the defaults of the detection path "
+                "(order 1, preserve_range, default anti-aliasing) are accelerated")
     shape = tuple(roi.shape)
     out_shape = isotropic_shape(shape, scale, res)
     edge = edge_mode_for(shape)

@@ -12,7 +12,7 @@ the image (``mmb_percentiles``), no host copy of the voxels.
 """
 from __future__ import annotations
 
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -91,14 +91,25 @@ def calc_near_bounds(image, dim_channel: int = 3):
 IMAGE5D_NP_VER = 15
 
 
-def make_filenames(filename: str, keep_ext: bool = False) -> Tuple[str, str]:
-    """``(<base>_image5d.npy, <base>_meta.yml)`` for an image path (importer.py:272-301;
-    no series / modifier, which the detection path never sets)."""
-    import os
+def filename_to_base(filename: str, series: Optional[int] = None, modifier: str = "",
+                     keep_ext: bool = False) -> str:
+    """Image path -> base path: the extension dropped unless ``keep_ext``, ``modifier``
+    appended after ``_``; ``series`` is ignored, as in the reference (importer.py:304-326)."""
+    from . import libmag
+    path = filename if keep_ext else libmag.splitext(filename)[0]
+    if modifier:
+        path = libmag.combine_paths(path, modifier, keep_ext=True)
+    return path
+
+
+def make_filenames(filename: str, series: Optional[int] = None, modifier: str = "",
+                   keep_ext: bool = False) -> Tuple[str, str]:
+    """``(<base>_image5d.npy, <base>_meta.yml)`` for an image path (importer.py:272-301)."""
     from . import libmag
     from ..settings import config
-    base = filename if keep_ext else os.path.splitext(filename)[0]
-    return (base + "_" + config.SUFFIX_IMAGE5D, base + "_" + config.SUFFIX_META)
+    base = filename_to_base(filename, series, modifier, keep_ext)
+    return (libmag.combine_paths(base, config.SUFFIX_IMAGE5D, keep_ext=True),
+            libmag.combine_paths(base, config.SUFFIX_META, keep_ext=True))
 
 
 def _primitive(val):
@@ -114,7 +125,7 @@ def _primitive(val):
         return val
 
 
-def save_image_info(filename_meta: str, names, sizes, resolutions, magnification, zoom,
+def save_image_info(filename_info_npz: str, names, sizes, resolutions, magnification, zoom,
                     near_min, near_max, scaling=None, plane=None) -> dict:
     """Write the image metadata as the reference's ``*_meta.yml`` (importer.py:482-522)."""
     import yaml
@@ -122,14 +133,45 @@ def save_image_info(filename_meta: str, names, sizes, resolutions, magnification
         "ver": IMAGE5D_NP_VER, "names": names, "sizes": sizes, "resolutions": resolutions,
         "magnification": magnification, "zoom": zoom, "near_min": near_min,
         "near_max": near_max, "scaling": scaling, "plane": plane})
-    with open(filename_meta, "w") as f:
+    with open(filename_info_npz, "w") as f:
         yaml.dump(data, f)
     return data
 
 
-def load_metadata(path: str, img5d=None):
-    """Read ``*_meta.yml`` (or the older ``.npz`` next to it) and assign resolutions,
-    magnification, zoom, ``near_min`` and ``near_max`` to ``config`` (importer.py:606-745).
+def assign_metadata(img5d, md: dict) -> None:
+    """Metadata dictionary -> ``img5d.shapes`` and the ``config`` globals the path reads
+    (resolutions, magnification, zoom, ``near_min``, ``near_max``), with the first series'
+    values under the ``config.MetaKeys`` entries (importer.py:671-745)."""
+    from ..settings import config
+
+    def first(val):
+        try:
+            return val[0]
+        except (TypeError, IndexError, KeyError):
+            return None
+    if "sizes" in md:
+        img5d.shapes = md["sizes"]
+        md[config.MetaKeys.SHAPE] = first(img5d.shapes)
+    if "resolutions" in md:
+        config.resolutions = np.array(md["resolutions"])
+        md[config.MetaKeys.RESOLUTIONS] = first(config.resolutions) \
+            if np.ndim(config.resolutions) else None
+    if "magnification" in md:
+        config.magnification = md["magnification"]
+        md[config.MetaKeys.MAGNIFICATION] = first(config.magnification)
+    if "zoom" in md:
+        config.zoom = md["zoom"]
+        md[config.MetaKeys.ZOOM] = first(config.zoom)
+    if "near_min" in md:
+        config.near_min = md["near_min"]
+    if "near_max" in md:
+        config.near_max = md["near_max"]
+
+
+def load_metadata(path: str, check_ver: bool = False, img5d=None):
+    """Read ``*_meta.yml`` (or the older ``.npz`` next to it); with ``img5d``, assign its
+    values to the image object and to ``config`` - unless ``check_ver`` and the file's
+    version is older than ``IMAGE5D_NP_VER`` (importer.py:606-668).
     Returns ``(metadata dict or None, version number or -1)``."""
     import os
     import yaml
@@ -139,6 +181,8 @@ def load_metadata(path: str, img5d=None):
         with open(path) as f:
             docs = list(yaml.load_all(f, Loader=yaml.FullLoader))
         output = docs[0] if docs else None
+        if output:
+            output.update(dict.fromkeys(config.MetaKeys, None))
     except FileNotFoundError:
         try:
             output = np_io.read_np_archive(np.load(f"{os.path.splitext(path)[0]}.npz"))
@@ -148,18 +192,7 @@ def load_metadata(path: str, img5d=None):
         return None, -1
     ver = output.get("ver", -1)
     ver = int(ver) if ver is not None else -1
-    if img5d is not None:
+    if img5d is not None and (not check_ver or ver >= IMAGE5D_NP_VER):
         img5d.meta = output
-        if "sizes" in output:
-            img5d.shapes = output["sizes"]
-    if output.get("resolutions") is not None:
-        config.resolutions = np.array(output["resolutions"])
-    if "magnification" in output:
-        config.magnification = output["magnification"]
-    if "zoom" in output:
-        config.zoom = output["zoom"]
-    if output.get("near_min") is not None:
-        config.near_min = output["near_min"]
-    if output.get("near_max") is not None:
-        config.near_max = output["near_max"]
+        assign_metadata(img5d, output)
     return output, ver

@@ -45,37 +45,46 @@ def read_np_archive(archive) -> Dict[str, Any]:
     return out
 
 
-def setup_images(path: str, series=None, subimg_offset=None, subimg_size=None) -> Image5d:
+def setup_images(path: str, series=None, offset=None, size=None, proc_type=None,
+                 allow_import: bool = True, fallback_main_img: bool = True, bg_atlas=None,
+                 labels_ref_path=None) -> Image5d:
     """Open the imported image of ``path`` for detection (the ``.npy`` route of
     np_io.py:193-592): memory-map ``<base>_image5d.npy`` read-only, load
     ``<base>_meta.yml`` into ``config`` (resolutions, ``near_min`` / ``near_max``,
-    magnification, zoom) and set ``config.filename``.  With ``subimg_offset`` /
-    ``subimg_size`` (z, y, x) the returned image is that view of the map, as the saved
-    sub-image route (:283-296) would hand over.
+    magnification, zoom) and set ``config.filename``.  With ``offset`` / ``size`` (z, y, x)
+    the returned image is that view of the map, as the saved sub-image route (:283-296)
+    would hand over.  The remaining parameters are the reference's; only their defaults are
+    served (no processing-type specific loading, no import of other formats, no atlas or
+    label images - all outside the accelerated path).
 
     Raises:
         FileNotFoundError: if the image file does not exist (other formats - TIFF, CZI
             import - are outside the accelerated path).
+        NotImplementedError: for ``proc_type``, ``bg_atlas`` or ``labels_ref_path``.
     """
     import os
     from . import importer
     from ..settings import config
+    for name, val in (("proc_type", proc_type), ("bg_atlas", bg_atlas),
+                      ("labels_ref_path", labels_ref_path)):
+        if val is not None:
+            raise NotImplementedError(f"setup_images({name}=...) is outside the detection path")
     base = path
     for suffix in ("_" + config.SUFFIX_IMAGE5D, "_" + config.SUFFIX_META):
         if base.endswith(suffix):
             base = base[:-len(suffix)]
-    filename_image5d, filename_meta = importer.make_filenames(base)
+    filename_image5d, filename_meta = importer.make_filenames(base, series)
     if not os.path.exists(filename_image5d):
-        filename_image5d, filename_meta = importer.make_filenames(base, keep_ext=True)
+        filename_image5d, filename_meta = importer.make_filenames(base, series, keep_ext=True)
     if not os.path.exists(filename_image5d):
         raise FileNotFoundError(f"no imported image {filename_image5d}")
     img5d = Image5d(np.load(filename_image5d, mmap_mode="r"), filename_image5d, filename_meta)
-    importer.load_metadata(filename_meta, img5d)
-    if subimg_offset is not None and subimg_size is not None:
-        z, y, x = (int(v) for v in subimg_offset)
-        sz, sy, sx = (int(v) for v in subimg_size)
+    importer.load_metadata(filename_meta, img5d=img5d)
+    if offset is not None and size is not None:
+        z, y, x = (int(v) for v in offset)
+        sz, sy, sx = (int(v) for v in size)
         img5d.img = img5d.img[:, z:z + sz, y:y + sy, x:x + sx]
-        img5d.subimg_offset, img5d.subimg_size = subimg_offset, subimg_size
+        img5d.subimg_offset, img5d.subimg_size = offset, size
     config.filename = path
     return img5d
 
@@ -92,7 +101,8 @@ def write_npy(image5d, md: Dict[Any, Any], path: str, find_near_bounds: bool = T
     # the reference keys the dictionary with `config.MetaKeys` members; plain lower-case
     # names are accepted as well
     md = {(k.name.lower() if isinstance(k, Enum) else k): v for k, v in md.items()}
-    filename_image5d, filename_meta = importer.make_filenames(os.path.splitext(path)[0],
+    from . import libmag
+    filename_image5d, filename_meta = importer.make_filenames(libmag.splitext(str(path))[0],
                                                               keep_ext=True)
     if os.path.exists(filename_image5d):
         print(f"File {filename_image5d} already exists, skipping saving image5d")

@@ -47,16 +47,16 @@ class SettingsDict(dict):
                 # YAML file are still useful to downstream readers, so keep them
                 self[key] = val
 
-    def get_profile(self, name: str) -> Optional[Dict]:
+    def get_profile(self, profile_name: str) -> Optional[Dict]:
         """Resolve a modifier by name or YAML path (profiles.py:160-216)."""
-        if os.path.splitext(name)[1].lower() in self._YAML_EXT:
-            path = os.path.join(self.PATH_PROFILES, name)
+        if os.path.splitext(profile_name)[1].lower() in self._YAML_EXT:
+            path = os.path.join(self.PATH_PROFILES, profile_name)
             if not os.path.exists(path):
-                path = name
+                path = profile_name
             if not os.path.exists(path):
                 # profiles shipped with this package
                 path = os.path.join(os.path.dirname(os.path.dirname(__file__)),
-                                    "profiles", os.path.basename(name))
+                                    "profiles", os.path.basename(profile_name))
                 if not os.path.exists(path):
                     return None
             self.timestamps[path] = os.path.getmtime(path)
@@ -66,9 +66,9 @@ class SettingsDict(dict):
                     if doc:
                         mods.update(doc)
             return mods
-        if name == self.DEFAULT_NAME:
+        if profile_name == self.DEFAULT_NAME:
             return self.__class__()
-        return self.profiles.get(name)
+        return self.profiles.get(profile_name)
 
     def add_profiles(self, names_str: str) -> None:
         for name in names_str.split(self.delimiter):

@@ -350,7 +350,7 @@ def test_setup_images_opens_reference_written_files(golden_dir):
     assert config.magnification == 20.0 and config.zoom == 1.0
     assert len(config.near_max) == 2 and len(config.near_min) == 2
     assert img5d.meta["ver"] == 15 and img5d.shapes == [[1, 6, 40, 36, 2]]
-    sub = nio.setup_images(base + "_image5d.npy", subimg_offset=(1, 4, 5), subimg_size=(3, 20, 10))
+    sub = nio.setup_images(base + "_image5d.npy", offset=(1, 4, 5), size=(3, 20, 10))
     assert sub.img.shape == (1, 3, 20, 10, 2)
     np.testing.assert_array_equal(sub.img[0], img5d.img[0, 1:4, 4:24, 5:15])
     with pytest.raises(FileNotFoundError):

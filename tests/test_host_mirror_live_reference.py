@@ -227,3 +227,83 @@ def test_write_npy_random_without_near_bounds(ns, seed, tmp_path):
     np.testing.assert_array_equal(np.asarray(img5d.img), img)
     assert [list(r) for r in config.resolutions] == res
     assert config.magnification == mag and config.zoom == zoom
+
+
+MIRRORED_MODULES = [
+    ("cv.detector", "magmap.cv.detector"), ("cv.stack_detect", "magmap.cv.stack_detect"),
+    ("cv.chunking", "magmap.cv.chunking"), ("plot.plot_3d", "magmap.plot.plot_3d"),
+    ("cv.cv_nd", "magmap.cv.cv_nd"), ("cv.colocalizer", "magmap.cv.colocalizer"),
+    ("io.np_io", "magmap.io.np_io"), ("io.importer", "magmap.io.importer"),
+    ("io.sqlite", "magmap.io.sqlite"), ("io.export_rois", "magmap.io.export_rois"),
+    ("io.libmag", "magmap.io.libmag"), ("settings.config", "magmap.settings.config"),
+    ("settings.roi_prof", "magmap.settings.roi_prof"),
+    ("settings.profiles", "magmap.settings.profiles"),
+]
+
+
+def test_every_mirrored_callable_has_the_reference_signature(ns):
+    """Every function, class and method the mirror defines under a name the reference module
+    also has takes the reference's parameters: same names in the same order, defaults where
+    the reference has defaults, the same kind of method.  (Names only the mirror has are its
+    own additions and are not checked.)"""
+    import importlib
+    import inspect
+
+    def params(fn):
+        try:
+            sig = inspect.signature(fn)
+        except (TypeError, ValueError):
+            return None
+        return [(p.name, p.kind, p.default is not inspect.Parameter.empty)
+                for p in sig.parameters.values()]
+
+    def compare(label, ours, theirs, problems):
+        a, b = params(ours), params(theirs)
+        if a is None or b is None:
+            return
+        var = (inspect.Parameter.VAR_POSITIONAL, inspect.Parameter.VAR_KEYWORD)
+        names_a = [p[0] for p in a if p[1] not in var]
+        names_b = [p[0] for p in b if p[1] not in var]
+        if names_a[:len(names_b)] != names_b:
+            problems.append(f"{label}: {names_a} vs reference {names_b}")
+            return
+        for pa, pb in zip([p for p in a if p[1] not in var], [p for p in b if p[1] not in var]):
+            if pa[2] != pb[2]:
+                problems.append(f"{label}: default of `{pa[0]}`")
+        for extra in [p for p in a if p[1] not in var][len(names_b):]:
+            if not extra[2]:
+                problems.append(f"{label}: extra parameter `{extra[0]}` without a default")
+        if {p[1] for p in b if p[1] in var} - {p[1] for p in a if p[1] in var}:
+            problems.append(f"{label}: reference takes *args / **kwargs")
+
+    problems, checked = [], 0
+    for ours_name, ref_name in MIRRORED_MODULES:
+        ours_mod = importlib.import_module("magellanmapper_b200." + ours_name)
+        ref_mod = importlib.import_module(ref_name)
+        for name, obj in vars(ours_mod).items():
+            if name.startswith("__") or getattr(obj, "__module__", None) != ours_mod.__name__:
+                continue
+            if not hasattr(ref_mod, name):
+                continue
+            ref_obj = getattr(ref_mod, name)
+            if inspect.isclass(obj):
+                for mname, member in vars(obj).items():
+                    if mname.startswith("__") and mname != "__init__":
+                        continue
+                    static = inspect.getattr_static(ref_obj, mname, None)
+                    if static is None or isinstance(member, property):
+                        continue
+                    fn = member.__func__ if isinstance(member, (classmethod, staticmethod)) else member
+                    ref_fn = static.__func__ if isinstance(static, (classmethod, staticmethod)) else static
+                    if not callable(fn) or not callable(ref_fn):
+                        continue
+                    if type(member).__name__ != type(static).__name__:
+                        problems.append(f"{ours_name}.{name}.{mname}: {type(member).__name__} vs "
+                                        f"reference {type(static).__name__}")
+                    compare(f"{ours_name}.{name}.{mname}", fn, ref_fn, problems)
+                    checked += 1
+            elif callable(obj):
+                compare(f"{ours_name}.{name}", obj, ref_obj, problems)
+                checked += 1
+    assert checked > 80
+    assert not problems, "\n".join(problems)
