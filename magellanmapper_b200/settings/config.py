@@ -32,8 +32,8 @@ near_max: List[float] = [-1.0]
 near_min: List[float] = [0.0]
 
 #: objective magnification and zoom of the loaded image (importer metadata)
-magnification = None
-zoom = None
+magnification = 1.0
+zoom = 1.0
 
 
 class MetaKeys(Enum):

@@ -307,3 +307,39 @@ def test_every_mirrored_callable_has_the_reference_signature(ns):
                 checked += 1
     assert checked > 80
     assert not problems, "\n".join(problems)
+
+
+def test_config_defaults_and_enums_equal_the_reference(ns):
+    """Every global the mirror's ``settings.config`` shares with the reference's starts with
+    the reference's value; the enums of the path list the same members."""
+    import enum
+    import inspect
+    from magellanmapper_b200.cv import stack_detect as sd
+    from magellanmapper_b200.settings import config as ours
+    theirs = ns.config
+    own = {"annotations", "gpu_device", "logger"}
+    # values the tests of this session may have assigned: compared on a fresh import instead
+    import importlib
+    fresh = importlib.util.module_from_spec(importlib.util.find_spec(ours.__name__))
+    fresh.__spec__.loader.exec_module(fresh)
+    ref_fresh = importlib.util.module_from_spec(importlib.util.find_spec(theirs.__name__))
+    ref_fresh.__spec__.loader.exec_module(ref_fresh)
+    for name, val in vars(fresh).items():
+        if name.startswith("_") or name in own or inspect.ismodule(val):
+            continue
+        if callable(val) and not inspect.isclass(val):
+            continue
+        assert hasattr(ref_fresh, name), f"config.{name} is not a reference global"
+        ref_val = getattr(ref_fresh, name)
+        if inspect.isclass(val):
+            if issubclass(val, enum.Enum):
+                assert [m.name for m in val] == [m.name for m in ref_val], name
+            continue
+        if isinstance(val, dict):
+            assert {str(k): v for k, v in val.items()} == {str(k): v for k, v in ref_val.items()}, name
+        else:
+            assert val == ref_val, f"config.{name}: {val!r} vs reference {ref_val!r}"
+    for a, b in ((detector.Blobs.Keys, ns.detector.Blobs.Keys), (detector.Blobs.Cols, ns.detector.Blobs.Cols),
+                 (sd.StackTimes, ns.stack_detect.StackTimes)):
+        assert [(m.name, m.value) for m in a] == [(m.name, m.value) for m in b]
+    assert detector.Blobs.BLOBS_NP_VER == ns.detector.Blobs.BLOBS_NP_VER
