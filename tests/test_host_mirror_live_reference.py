@@ -343,3 +343,57 @@ def test_config_defaults_and_enums_equal_the_reference(ns):
                  (sd.StackTimes, ns.stack_detect.StackTimes)):
         assert [(m.name, m.value) for m in a] == [(m.name, m.value) for m in b]
     assert detector.Blobs.BLOBS_NP_VER == ns.detector.Blobs.BLOBS_NP_VER
+
+
+def test_error_behaviour_equals_the_reference(ns, tmp_path):
+    """Bad calls into the host-only part of the path end the same way in both: the same
+    exception type, or both succeed with the same kind of result."""
+    import importlib
+    from magellanmapper_b200.cv import chunking, stack_detect as sd
+    from magellanmapper_b200.io import importer, libmag, np_io
+    from magellanmapper_b200.settings import roi_prof
+    ref_importer = importlib.import_module("magmap.io.importer")
+    ref_libmag = importlib.import_module("magmap.io.libmag")
+    tmp = str(tmp_path)
+
+    def outcome(fn):
+        try:
+            return "ok", type(fn()).__name__
+        except Exception as e:                                   # noqa: BLE001
+            return (type(e).__name__,)
+
+    empty_grid = np.zeros((1, 1, 1), dtype=object)
+    cases = [
+        (lambda: detector.Blobs().load_blobs(tmp + "/nope.npz"),
+         lambda: ns.detector.Blobs().load_blobs(tmp + "/nope.npz")),
+        (lambda: chunking.stack_splitter((4, 4), (2, 2)), lambda: ns.chunking.stack_splitter((4, 4), (2, 2))),
+        (lambda: chunking.merge_blobs(empty_grid), lambda: ns.chunking.merge_blobs(empty_grid)),
+        (lambda: detector.Blobs(None).format_blobs(), lambda: ns.detector.Blobs(None).format_blobs()),
+        (lambda: detector.get_blobs_in_roi(None, (0, 0, 0), (1, 1, 1)),
+         lambda: ns.detector.get_blobs_in_roi(None, (0, 0, 0), (1, 1, 1))),
+        (lambda: detector.remove_close_blobs(None, np.zeros((2, 4)), (1, 1, 1)),
+         lambda: ns.detector.remove_close_blobs(None, np.zeros((2, 4)), (1, 1, 1))),
+        (lambda: detector.remove_close_blobs(np.zeros((2, 4)), None, (1, 1, 1)),
+         lambda: ns.detector.remove_close_blobs(np.zeros((2, 4)), None, (1, 1, 1))),
+        (lambda: detector.sort_blobs(np.zeros((0, 4))), lambda: ns.detector.sort_blobs(np.zeros((0, 4)))),
+        (lambda: detector.meas_pruning_ratio(None, 1, 1), lambda: ns.detector.meas_pruning_ratio(None, 1, 1)),
+        (lambda: importer.load_metadata(tmp + "/no_meta.yml"),
+         lambda: ref_importer.load_metadata(tmp + "/no_meta.yml")),
+        (lambda: libmag.combine_paths(None, "x"), lambda: ref_libmag.combine_paths(None, "x")),
+        (lambda: roi_prof.ROIProfile().add_profiles("nonesuch"),
+         lambda: ns.roi_prof.ROIProfile().add_profiles("nonesuch")),
+        (lambda: np_io.get_num_channels(None), lambda: ns.np_io.get_num_channels(None)),
+        (lambda: sd.detect_blobs_stack("x", None), lambda: ns.stack_detect.detect_blobs_stack("x", None)),
+        (lambda: sd.detect_blobs_blocks("x", np_io.Image5d(None)),
+         lambda: ns.stack_detect.detect_blobs_blocks("x", ns.np_io.Image5d(None))),
+    ]
+    config.resolutions = ns.config.resolutions = [[1.0, 1.0, 1.0]]
+    for i, (ours, theirs) in enumerate(cases):
+        assert outcome(ours) == outcome(theirs), i
+    config.resolutions = ns.config.resolutions = None
+    for ours, theirs in (
+            (detector.calc_overlap, ns.detector.calc_overlap),
+            (lambda: sd.setup_blocks(roi_prof.ROIProfile(), (10, 10, 10)),
+             lambda: ns.stack_detect.setup_blocks(ns.roi_prof.ROIProfile(), (10, 10, 10)))):
+        assert outcome(ours) == outcome(theirs) == ("AttributeError",)
+    config.resolutions = ns.config.resolutions = [[1.0, 1.0, 1.0]]
