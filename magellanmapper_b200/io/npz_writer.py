@@ -170,27 +170,39 @@ def savez(path, arrays: Dict[str, object], add_suffix: bool = True) -> None:
         if mapped is not None:
             dst = np.frombuffer(mapped, dtype=np.uint8)
             jobs = []
-            for e in entries:
-                if e.data is None:
-                    continue
-                lead = len(e.local_header(dos_time, dos_date)) + len(e.head)
-                src = np.frombuffer(e.data, dtype=np.uint8)
-                base = e.offset + lead
-                for lo in range(0, len(src), _PIECE):
-                    hi = min(lo + _PIECE, len(src))
-                    jobs.append(ex.submit(np.copyto, dst[base + lo:base + hi], src[lo:hi]))
-            for j in jobs:
-                j.result()
-            jobs.clear()
-            src = None
-            finish_crcs()
-            for e in entries:
-                head = e.local_header(dos_time, dos_date) + e.head
-                mapped[e.offset:e.offset + len(head)] = head
-            tail = directory()
-            mapped[cd_offset:cd_offset + len(tail)] = tail
-            del dst
-            mapped.close()
+            try:
+                for e in entries:
+                    if e.data is None:
+                        continue
+                    lead = len(e.local_header(dos_time, dos_date)) + len(e.head)
+                    src = np.frombuffer(e.data, dtype=np.uint8)
+                    base = e.offset + lead
+                    for lo in range(0, len(src), _PIECE):
+                        hi = min(lo + _PIECE, len(src))
+                        jobs.append(ex.submit(np.copyto, dst[base + lo:base + hi], src[lo:hi]))
+                for j in jobs:
+                    j.result()
+                finish_crcs()
+                for e in entries:
+                    head = e.local_header(dos_time, dos_date) + e.head
+                    mapped[e.offset:e.offset + len(head)] = head
+                tail = directory()
+                mapped[cd_offset:cd_offset + len(tail)] = tail
+            finally:
+                # every view of the mapping has to go before it can be closed
+                for j in jobs:
+                    j.cancel()
+                for j in jobs:
+                    if not j.cancelled():
+                        j.exception()
+                jobs.clear()
+                src = dst = None
+                try:
+                    mapped.close()
+                except BufferError:
+                    # a propagating exception's traceback still holds a view of the mapping;
+                    # the mapping goes with it
+                    pass
         else:
             finish_crcs()
             with os.fdopen(os.dup(fd), "wb") as f:
