@@ -397,3 +397,68 @@ def test_error_behaviour_equals_the_reference(ns, tmp_path):
              lambda: ns.stack_detect.setup_blocks(ns.roi_prof.ROIProfile(), (10, 10, 10)))):
         assert outcome(ours) == outcome(theirs) == ("AttributeError",)
     config.resolutions = ns.config.resolutions = [[1.0, 1.0, 1.0]]
+
+
+def _np_find_close(blobs, master, tol):
+    """numpy stand-in for the GPU box match (the contract of detector._find_close_blobs)."""
+    c = np.asarray(blobs)[:, :3].astype(np.int32)
+    m = np.asarray(master)[:, :3].astype(np.int32)
+    close = np.all(np.abs(m[:, None, :] - c[None, :, :]) <= np.asarray(tol)[None, None, :], axis=2)
+    hit = close.any(axis=0)
+    last = np.where(close.any(axis=1), close.shape[1] - 1 - np.argmax(close[:, ::-1], axis=1), -1)
+    return last.astype(np.int64), hit
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_host_route_merge_and_prune_random_grids(ns, seed, monkeypatch):
+    """The mirror's own ``merge_blobs`` + index-form ``StackPruner.prune_blobs_mp`` +
+    ``remove_close_blobs`` bookkeeping (the GPU box match replaced by numpy) against the
+    unmodified reference on random, ragged, anisotropic grids with one or two channels:
+    the same table row for row and the same pruning-ratio frame."""
+    from oracle import ref_shim
+    from magellanmapper_b200.cv import chunking, stack_detect as sd
+    from magellanmapper_b200.settings import roi_prof
+    monkeypatch.setattr(detector, "_find_close_blobs", _np_find_close)
+    rng = np.random.default_rng(300 + seed)
+    shape = tuple(int(v) for v in rng.integers(40, 150, 3))
+    res = [float(v) for v in rng.choice([0.7, 1.0, 2.0, 5.0], 3)]
+    mods = {"segment_size": int(rng.integers(25, 70)),
+            "prune_tol_factor": tuple(float(v) for v in rng.choice([0.9, 1.0, 1.6], 3))}
+    ref_prof = ref_shim.set_profile(ns, res, **mods)
+    rb = ns.stack_detect.setup_blocks(ref_prof, shape)
+    prof = roi_prof.ROIProfile()
+    prof.add_profiles("roi_blobs.yaml")
+    for k, v in mods.items():
+        prof[k] = v
+    config.roi_profile, config.roi_profiles, config.resolutions = prof, [prof], [res]
+    ob = sd.setup_blocks(prof, shape)
+    n_chl = 1 + seed % 2
+    base = rng.integers(0, shape, (int(rng.integers(300, 1500)), 3)).astype(float)
+    seg_a = np.zeros(rb.sub_roi_slices.shape, dtype=object)
+    seg_b = np.zeros(rb.sub_roi_slices.shape, dtype=object)
+    for c in np.ndindex(*seg_a.shape):
+        sl = rb.sub_roi_slices[c]
+        inside = np.all([(base[:, a] >= sl[a].start) & (base[:, a] < sl[a].stop)
+                         for a in range(3)], axis=0)
+        pts = base[inside] + rng.integers(-2, 3, (int(inside.sum()), 3))
+        pts = np.clip(pts, [s.start for s in sl], [s.stop - 1 for s in sl])
+        if len(pts) == 0:
+            seg_a[c] = seg_b[c] = None
+            continue
+        t = np.full((len(pts), 11), -1.0)
+        t[:, :3] = pts
+        t[:, 3] = rng.uniform(4, 9, len(pts))
+        t[:, 6] = rng.integers(0, n_chl, len(pts))
+        t[:, 7:10] = pts
+        seg_a[c], seg_b[c] = t.copy(), t.copy()
+    np.testing.assert_array_equal(chunking.merge_blobs(seg_a), ns.chunking.merge_blobs(seg_b))
+    channels = list(range(n_chl))
+    want, want_df = ns.stack_detect.StackPruner.prune_blobs_mp(
+        np.zeros(shape, np.uint8), seg_b, rb.overlap, rb.tol, rb.sub_roi_slices,
+        rb.sub_rois_offsets, channels, rb.overlap_padding)
+    got, got_df = sd.StackPruner.prune_blobs_mp(
+        None, seg_a, ob.overlap, ob.tol, ob.sub_roi_slices, ob.sub_rois_offsets, channels,
+        ob.overlap_padding)
+    np.testing.assert_array_equal(got, want)
+    assert list(got_df.columns) == list(want_df.columns)
+    np.testing.assert_allclose(got_df.to_numpy(dtype=float), want_df.to_numpy(dtype=float))
