@@ -419,6 +419,10 @@ def test_host_route_merge_and_prune_random_grids(ns, seed, monkeypatch):
     from magellanmapper_b200.cv import chunking, stack_detect as sd
     from magellanmapper_b200.settings import roi_prof
     monkeypatch.setattr(detector, "_find_close_blobs", _np_find_close)
+    # the column map is class-level state that every `Blobs` constructor rewrites (as in the
+    # reference, detector.py:116, 142-162); detection always leaves the full set behind
+    detector.Blobs().cols = [c.value for c in detector.Blobs.Cols]
+    ns.detector.Blobs().cols = [c.value for c in ns.detector.Blobs.Cols]
     rng = np.random.default_rng(300 + seed)
     shape = tuple(int(v) for v in rng.integers(40, 150, 3))
     res = [float(v) for v in rng.choice([0.7, 1.0, 2.0, 5.0], 3)]
