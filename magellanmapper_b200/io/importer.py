@@ -96,10 +96,8 @@ def filename_to_base(filename: str, series: Optional[int] = None, modifier: str 
     """Image path -> base path: the extension dropped unless ``keep_ext``, ``modifier``
     appended after ``_``; ``series`` is ignored, as in the reference (importer.py:304-326)."""
     from . import libmag
-    path = filename if keep_ext else libmag.splitext(filename)[0]
-    if modifier:
-        path = libmag.combine_paths(path, modifier, keep_ext=True)
-    return path
+    base = filename if keep_ext else libmag.splitext(filename)[0]
+    return libmag.combine_paths(base, modifier, keep_ext=True) if modifier else base
 
 
 def make_filenames(filename: str, series: Optional[int] = None, modifier: str = "",

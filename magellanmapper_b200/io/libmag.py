@@ -64,62 +64,62 @@ _FILE_TYPE_GROUPS = {"obj": "mtl", "mhd": "raw"}
 
 
 def splitext(path):
-    """``os.path.splitext`` that keeps multi-period extensions such as ``.nii.gz`` whole
-    (libmag.py:272-293)."""
-    i = -1
-    for ext in _EXTENSIONS_MULTIPLE:
-        i = path.rfind(ext)
-        if i != -1:
-            break
-    return os.path.splitext(path) if i == -1 else (path[:i], path[i:])
+    """``os.path.splitext`` that keeps multi-period extensions such as ``.nii.gz`` whole:
+    the split is at the last occurrence of the first listed extension start that the path
+    contains (libmag.py:272-293)."""
+    for start in _EXTENSIONS_MULTIPLE:
+        at = path.rfind(start)
+        if at >= 0:
+            return path[:at], path[at:]
+    return os.path.splitext(path)
 
 
 def insert_before_ext(name, insert: str, sep: str = "") -> str:
-    """Splice ``insert`` in front of the extension of ``name`` (libmag.py:247-269)."""
+    """``name`` with ``sep + insert`` spliced in front of its last extension; appended
+    when the base name has no period (libmag.py:247-269)."""
     name = str(name)
-    if os.path.basename(name).find(".") == -1:
-        return name + sep + insert
-    return "{0}{2}{3}.{1}".format(*name.rsplit(".", 1), sep, insert)
+    if "." not in os.path.basename(name):
+        return f"{name}{sep}{insert}"
+    stem, _, ext = name.rpartition(".")
+    return f"{stem}{sep}{insert}.{ext}"
 
 
 def combine_paths(base_path: Optional[str], suffix: str, sep: str = "_",
                   ext: Optional[str] = None, check_dir: bool = False,
                   keep_ext: bool = False) -> str:
     """``base_path`` (without its extension unless ``keep_ext``) + ``sep`` + ``suffix``; a
-    directory (trailing separator, or an existing one with ``check_dir``) is joined instead;
-    ``ext`` replaces the extension of the result (libmag.py:331-369)."""
+    directory - a trailing separator, or an existing directory when ``check_dir`` - is
+    joined with ``suffix`` instead; ``ext`` replaces the extension of the result; no base
+    path gives ``suffix`` (libmag.py:331-369)."""
     if not base_path:
         return suffix
-    if not os.path.basename(base_path) or check_dir and os.path.isdir(base_path):
-        path = os.path.join(base_path, suffix)
+    is_dir = not os.path.basename(base_path) or (check_dir and os.path.isdir(base_path))
+    if is_dir:
+        out = os.path.join(base_path, suffix)
     else:
-        path = base_path if keep_ext else splitext(base_path)[0]
-        path = path + sep + suffix
-    if ext:
-        path = f"{splitext(path)[0]}.{ext}"
-    return path
+        stem = base_path if keep_ext else splitext(base_path)[0]
+        out = f"{stem}{sep}{suffix}"
+    return f"{splitext(out)[0]}.{ext}" if ext else out
 
 
 def backup_file(path, modifier: str = "", i: Optional[int] = None) -> None:
-    """Move an existing file to ``name[modifier](i).ext`` with the first free ``i`` - to
-    ``name[modifier].ext`` itself when a modifier is given and that name is free - and do
-    the same, with the same index, for a file that travels with it (libmag.py:969-1015)."""
-    if not i:
-        if not os.path.exists(path):
-            return
-        i = 0
+    """Move an existing file out of the way: to ``name<modifier>.ext`` when a modifier is
+    given and that name is free, else to ``name<modifier>(n).ext`` with the first free
+    ``n >= 1``.  A file that travels with it (``.mtl`` of an ``.obj``, ``.raw`` of an
+    ``.mhd``) is moved the same way starting from the same ``n``, which is what ``i`` is
+    for (libmag.py:969-1015)."""
+    n = int(i) if i else 0
+    if n == 0 and not os.path.exists(path):
+        return
     while True:
-        if i == 0 and modifier != "":
-            backup_path = insert_before_ext(path, modifier)
-        else:
-            if i == 0:
-                i = 1
-            backup_path = insert_before_ext(path, "{}({})".format(modifier, i))
-        if not os.path.exists(backup_path):
-            shutil.move(path, backup_path)
-            root, ext = os.path.splitext(path)
-            associated = _FILE_TYPE_GROUPS.get(ext[1:])
-            if associated:
-                backup_file("{}.{}".format(root, associated), modifier, i)
+        if n == 0 and modifier == "":
+            n = 1
+        target = insert_before_ext(path, modifier if n == 0 else f"{modifier}({n})")
+        if not os.path.exists(target):
             break
-        i += 1
+        n += 1
+    shutil.move(path, target)
+    stem, ext = os.path.splitext(path)
+    partner = _FILE_TYPE_GROUPS.get(ext[1:])
+    if partner:
+        backup_file(f"{stem}.{partner}", modifier, n)

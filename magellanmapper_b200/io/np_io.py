@@ -31,8 +31,10 @@ class Image5d:
 def get_num_channels(img=None, is_3d: bool = False) -> int:
     """Channel count of a ``t,z,y,x[,c]`` image, or of a ``z,y,x[,c]`` one with ``is_3d``
     (np_io.py:610-625)."""
-    chl_dim = 3 if is_3d else 4
-    return 1 if img is None or img.ndim <= chl_dim else img.shape[chl_dim]
+    axis = 3 if is_3d else 4
+    if img is None or img.ndim <= axis:
+        return 1
+    return int(img.shape[axis])
 
 
 def read_np_archive(archive) -> Dict[str, Any]:

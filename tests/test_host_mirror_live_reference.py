@@ -466,3 +466,51 @@ def test_host_route_merge_and_prune_random_grids(ns, seed, monkeypatch):
     np.testing.assert_array_equal(got, want)
     assert list(got_df.columns) == list(want_df.columns)
     np.testing.assert_allclose(got_df.to_numpy(dtype=float), want_df.to_numpy(dtype=float))
+
+
+def test_path_helpers_and_backup_rule_random(ns, tmp_path):
+    """``libmag.splitext`` / ``insert_before_ext`` / ``combine_paths`` on a few hundred
+    generated paths, and ``backup_file`` replayed in two directories (plain, with a modifier,
+    repeated, with a companion file): the same strings and the same directory listings."""
+    import importlib
+    import itertools
+    from magellanmapper_b200.io import libmag
+    ref = importlib.import_module("magmap.io.libmag")
+    stems = ["item", "foo/bar/item", "foo.d/bar", "a.b/c.d/e", "x/", "", "img.nii", "vol.nii.gz",
+             "arch.tar.gz", "deep/er.tar/thing", ".hidden", "dir.with.dots/plain"]
+    exts = ["", ".py", ".npz", ".file.ext", ".nii.gz", ".tar"]
+    for stem, ext in itertools.product(stems, exts):
+        path = stem + ext
+        assert libmag.splitext(path) == ref.splitext(path), path
+        for insert, sep in (("totest", "_"), ("(1)", ""), ("a.b", "-")):
+            assert libmag.insert_before_ext(path, insert, sep) == ref.insert_before_ext(path, insert, sep)
+        for suffix, sep, new_ext, keep in (("file.py", "_", None, False), ("blobs.npz", "_", None, True),
+                                           ("file", "-", "ext", False), ("image5d.npy", "_", "npz", True)):
+            for base in (path, None):
+                assert (libmag.combine_paths(base, suffix, sep, new_ext, False, keep)
+                        == ref.combine_paths(base, suffix, sep, new_ext, False, keep)), (base, suffix)
+    existing = str(tmp_path)
+    assert libmag.combine_paths(existing, "x.npz", check_dir=True) == \
+        ref.combine_paths(existing, "x.npz", check_dir=True)
+
+    listings = []
+    for tag, mod in (("ours", libmag), ("theirs", ref)):
+        d = tmp_path / tag
+        d.mkdir()
+
+        def touch(name):
+            (d / name).write_text(name)
+        for _ in range(3):                                   # plain: (1), (2), (3)
+            touch("s_blobs.npz")
+            mod.backup_file(str(d / "s_blobs.npz"))
+        for _ in range(3):                                   # modifier: _old, _old(1), _old(2)
+            touch("t.csv")
+            mod.backup_file(str(d / "t.csv"), "_old")
+        for _ in range(2):                                   # companion file moves along
+            touch("mesh.obj")
+            touch("mesh.mtl")
+            mod.backup_file(str(d / "mesh.obj"))
+        mod.backup_file(str(d / "absent.npz"))               # nothing to do
+        listings.append(sorted((p.name, p.read_text()) for p in d.iterdir()))
+    assert listings[0] == listings[1]
+    assert ("s_blobs(3).npz", "s_blobs.npz") in listings[0] and ("t_old(2).csv", "t.csv") in listings[0]
