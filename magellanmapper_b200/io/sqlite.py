@@ -82,18 +82,19 @@ def insert_roi(conn, cur, exp_id: int, series: Optional[int], offset: Sequence[i
 
 
 def select_or_insert_roi(conn, cur, exp_id: int, series: Optional[int], offset, size):
-    """sqlite.py:270-300."""
-    stmnt = ("SELECT * FROM rois WHERE experiment_id = ? AND offset_x = ? AND offset_y = ? "
-             "AND offset_z = ? AND size_x = ? AND size_y = ? AND size_z = ?")
-    args = [exp_id, *[int(v) for v in offset], *[int(v) for v in size]]
+    """The id of the ROI with this experiment, offset and size (and series, when one is
+    given), inserting it when there is none; returns ``(id, message)`` (sqlite.py:270-300)."""
+    where = {"experiment_id": exp_id}
+    where.update(zip(("offset_x", "offset_y", "offset_z"), (int(v) for v in offset)))
+    where.update(zip(("size_x", "size_y", "size_z"), (int(v) for v in size)))
     if series is not None:
-        stmnt += " AND series = ?"
-        args.append(series)
-    cur.execute(stmnt, args)
-    row = cur.fetchone()
-    if row is not None and len(row) > 0:
-        return row[0], "Found ROI {}".format(row[0])
-    return insert_roi(conn, cur, exp_id, series, offset, size)
+        where["series"] = series
+    cur.execute("SELECT * FROM rois WHERE " + " AND ".join(f"{k} = ?" for k in where),
+                list(where.values()))
+    found = cur.fetchone()
+    if found is None or len(found) == 0:
+        return insert_roi(conn, cur, exp_id, series, offset, size)
+    return found[0], "Found ROI {}".format(found[0])
 
 
 def insert_blobs(conn, cur, roi_id: int, blobs) -> int:
@@ -126,17 +127,17 @@ def delete_blobs(conn, cur, roi_id: int, blobs) -> int:
     return deleted
 
 
+_BLOB_FIELDS = ("z", "y", "x", "radius", "confirmed", "truth", "channel")
+
+
 def _parse_blobs(rows):
     """Rows -> ``(n, 7)`` table ``z, y, x, radius, confirmed, truth, channel`` and the row
-    ids (sqlite.py:415-435)."""
-    blobs = np.empty((len(rows), 7))
-    ids = []
-    for i, row in enumerate(rows):
-        blobs[i] = [row["z"], row["y"], row["x"], row["radius"], row["confirmed"],
-                    row["truth"], row["channel"]]
-        if "id" in row.keys():
-            ids.append(row["id"])
-    return blobs, ids
+    ids of the rows that carry one (sqlite.py:415-435)."""
+    table = np.empty((len(rows), len(_BLOB_FIELDS)))
+    for out, row in zip(table, rows):
+        out[:] = [row[f] for f in _BLOB_FIELDS]
+    ids = [row["id"] for row in rows if "id" in row.keys()]
+    return table, ids
 
 
 def select_blobs_by_roi(cur, roi_id: int):
